@@ -1,0 +1,19 @@
+"""mgb200: B200-native (sm_100a) mixed-precision geometric multigrid V/W-cycle hot path.
+
+Drop-in for the reference's ``multigrid.core`` / ``.operators`` / ``.solvers`` surface on this path
+(see SURVEY.md section 8).  All arithmetic runs in hand-written CUDA kernels behind the C ABI of
+``include/mgb200.h`` (libmgb200.so); there is no CPU fallback."""
+from . import ops
+from ._lib import LIB_PATH, MGLibraryError
+from .core import Grid, PrecisionLevel, PrecisionManager
+from .operators import BaseOperator, LaplacianOperator, ProlongationOperator, RestrictionOperator
+from .solvers import (BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
+                      MultigridCycle, MultigridSolver, SymmetricGaussSeidelSmoother, WeightedJacobiSmoother)
+
+__version__ = "0.1.0"
+GPU_AVAILABLE = True  # the only path there is
+
+__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "RestrictionOperator",
+           "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
+           "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
+           "SymmetricGaussSeidelSmoother", "MGLibraryError", "ops", "LIB_PATH"]

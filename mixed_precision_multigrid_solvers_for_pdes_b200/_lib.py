@@ -1,0 +1,75 @@
+"""ctypes binding of libmgb200.so (include/mgb200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an
+exception is raised.  The product path never routes through ``oracle/`` or any CPU code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmgb200.so")
+
+F32, F64 = 0, 1
+RESTRICT = {"full_weighting": 0, "injection": 1, "half_weighting": 2}
+PROLONG = {"bilinear": 0, "injection": 1}
+
+_i, _l, _d, _p = C.c_int, C.c_int64, C.c_double, C.c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPE); mirrors include/mgb200.h
+SIGNATURES = {
+    "mg_abi_version": [],
+    "mg_status_string": [_i],
+    "mg_device_sm_count": [],
+    "mg_apply_laplacian": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _p],
+    "mg_residual": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _i, _i, _p],
+    "mg_smooth_rbgs": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _i, _p],
+    "mg_smooth_jacobi": [_p, _p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _i, _p],
+    "mg_smooth_lexgs": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _i, _i, _p],
+    "mg_coarse_solve_lexgs": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _d, _d, _i, _p, _i, _p],
+    "mg_restrict": [_p, _p, _i, _i, _l, _l, _i, _i, _i, _p],
+    "mg_prolong": [_p, _p, _i, _i, _l, _l, _i, _i, _i, _i, _p],
+    "mg_sumsq": [_p, _i, _i, _l, _i, _p, _p, _p],
+    "mg_sumsq_workspace_doubles": [],
+    "mg_cast": [_p, _p, _i, _i, _l, _l, _i, _i, _p],
+    "mg_axpy": [_d, _p, _p, _i, _i, _l, _l, _i, _i, _p],
+    "mg_zero": [_p, _i, _l, _i, _p],
+    "mg_fill_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p],
+    "mg_maxerr_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p, _p, _p],
+}
+_RESTYPE = {"mg_status_string": C.c_char_p}
+_NO_STATUS = {"mg_abi_version", "mg_status_string", "mg_device_sm_count", "mg_sumsq_workspace_doubles"}
+
+_lib: Optional[C.CDLL] = None
+
+
+class MGLibraryError(RuntimeError):
+    """libmgb200.so is missing or a kernel call returned an error status."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MGLibraryError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C mixed_precision_multigrid_solvers_for_pdes_b200/csrc`). There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.argtypes = args
+            fn.restype = _RESTYPE.get(name, C.c_int)
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> int:
+    """Invoke an entry point; raise MGLibraryError on a non-zero status."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if name not in _NO_STATUS and rc != 0:
+        msg = lib.mg_status_string(rc)
+        raise MGLibraryError(f"{name} failed with status {rc}: {msg.decode() if msg else '?'}")
+    return rc

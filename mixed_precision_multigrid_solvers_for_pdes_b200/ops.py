@@ -1,0 +1,176 @@
+"""Functional layer over the C ABI: one Python function per libmgb200 entry point, operating on
+pitched CUDA tensors (see device.py).  Functions ending in ``_`` work in place.  All launches go
+to torch's current stream, so they compose with CUDA-graph capture and torch.distributed."""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .device import code, empty_field, ld, stream_ptr, torch_dtype
+
+_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(dev: torch.device) -> torch.Tensor:
+    """Per-(device, stream) reduction scratch: partials followed by 8 result slots."""
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr())
+    w = _ws.get(key)
+    if w is None:
+        n = _lib.call("mg_sumsq_workspace_doubles")
+        w = torch.zeros(n + 8, dtype=torch.float64, device=dev)
+        _ws[key] = w
+    return w
+
+
+def _check_same_shape(a: torch.Tensor, b: torch.Tensor, what: str) -> None:
+    if a.shape != b.shape:
+        raise ValueError(f"{what}: shapes {tuple(a.shape)} and {tuple(b.shape)} differ")
+
+
+def apply_laplacian(u: torch.Tensor, hx: float, hy: float, coefficient: float = 1.0,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    nx, ny = u.shape
+    if out is None:
+        out = empty_field(nx, ny, u.dtype, u.device, zero=False)
+    _lib.call("mg_apply_laplacian", u.data_ptr(), out.data_ptr(), nx, ny, ld(u), ld(out), hx, hy, coefficient,
+              code(u.dtype), stream_ptr())
+    return out
+
+
+def residual(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, coefficient: float = 1.0,
+             out: Optional[torch.Tensor] = None, out_dtype=None) -> torch.Tensor:
+    _check_same_shape(u, f, "residual")
+    if u.dtype != f.dtype:
+        raise TypeError("residual: u and f must share a dtype")
+    nx, ny = u.shape
+    if out is None:
+        out = empty_field(nx, ny, out_dtype or u.dtype, u.device, zero=False)
+    _lib.call("mg_residual", u.data_ptr(), f.data_ptr(), out.data_ptr(), nx, ny, ld(u), ld(f), ld(out), hx, hy,
+              coefficient, code(u.dtype), code(out.dtype), stream_ptr())
+    return out
+
+
+def smooth_rbgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0, sweeps: int = 1):
+    _check_same_shape(u, f, "smooth_rbgs")
+    nx, ny = u.shape
+    _lib.call("mg_smooth_rbgs", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, sweeps,
+              code(u.dtype), stream_ptr())
+    return u
+
+
+def smooth_jacobi_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 2.0 / 3.0,
+                   sweeps: int = 1, tmp: Optional[torch.Tensor] = None):
+    _check_same_shape(u, f, "smooth_jacobi")
+    nx, ny = u.shape
+    if tmp is None or ld(tmp) != ld(u):
+        tmp = torch.empty_strided((nx, ny), (ld(u), 1), dtype=u.dtype, device=u.device)
+    _lib.call("mg_smooth_jacobi", u.data_ptr(), tmp.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega,
+              sweeps, code(u.dtype), stream_ptr())
+    return u
+
+
+LEXGS_MODES = {"forward": 0, "backward": 1, "symmetric": 2}
+
+
+def smooth_lexgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0, sweeps: int = 1,
+                  mode: str = "forward"):
+    _check_same_shape(u, f, "smooth_lexgs")
+    nx, ny = u.shape
+    _lib.call("mg_smooth_lexgs", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, sweeps,
+              LEXGS_MODES[mode], code(u.dtype), stream_ptr())
+    return u
+
+
+def coarse_solve_lexgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0,
+                        coefficient: float = -1.0, tolerance: float = 1e-12, max_iterations: int = 1000,
+                        info: Optional[torch.Tensor] = None):
+    """`info`: optional device tensor of >= 2 float64 receiving (sweeps done, last norm)."""
+    _check_same_shape(u, f, "coarse_solve")
+    nx, ny = u.shape
+    _lib.call("mg_coarse_solve_lexgs", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, coefficient,
+              tolerance, max_iterations, info.data_ptr() if info is not None else None, code(u.dtype), stream_ptr())
+    return u
+
+
+def restrict(fine: torch.Tensor, method: str = "full_weighting", out: Optional[torch.Tensor] = None,
+             out_dtype=None) -> torch.Tensor:
+    nxf, nyf = fine.shape
+    nxc, nyc = (nxf - 1) // 2 + 1, (nyf - 1) // 2 + 1
+    if out is None:
+        out = empty_field(nxc, nyc, out_dtype or fine.dtype, fine.device, zero=False)
+    elif tuple(out.shape) != (nxc, nyc):
+        raise ValueError(f"Cannot restrict from {tuple(fine.shape)} to {tuple(out.shape)}")
+    _lib.call("mg_restrict", fine.data_ptr(), out.data_ptr(), nxf, nyf, ld(fine), ld(out), _lib.RESTRICT[method],
+              code(fine.dtype), code(out.dtype), stream_ptr())
+    return out
+
+
+def prolong(coarse: torch.Tensor, method: str = "bilinear", out: Optional[torch.Tensor] = None, add: bool = False,
+            out_dtype=None) -> torch.Tensor:
+    nxc, nyc = coarse.shape
+    nxf, nyf = 2 * (nxc - 1) + 1, 2 * (nyc - 1) + 1
+    if out is None:
+        if add:
+            raise ValueError("prolong(add=True) needs the fine field to add to")
+        out = empty_field(nxf, nyf, out_dtype or coarse.dtype, coarse.device, zero=False)
+    elif tuple(out.shape) != (nxf, nyf):
+        raise ValueError(f"Cannot prolongate from {tuple(coarse.shape)} to {tuple(out.shape)}")
+    _lib.call("mg_prolong", coarse.data_ptr(), out.data_ptr(), nxc, nyc, ld(coarse), ld(out), _lib.PROLONG[method],
+              1 if add else 0, code(coarse.dtype), code(out.dtype), stream_ptr())
+    return out
+
+
+def sumsq_async(x: torch.Tensor, slot: int = 0) -> torch.Tensor:
+    """Launch the deterministic sum of squares; returns a 1-element device view (no sync)."""
+    w = _workspace(x.device)
+    n = w.numel() - 8
+    out = w[n + slot:n + slot + 1]
+    nx, ny = x.shape
+    _lib.call("mg_sumsq", x.data_ptr(), nx, ny, ld(x), code(x.dtype), w.data_ptr(), out.data_ptr(), stream_ptr())
+    return out
+
+
+def sumsq(x: torch.Tensor) -> float:
+    return float(sumsq_async(x).item())
+
+
+def cast(x: torch.Tensor, dtype, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    tdt = torch_dtype(dtype)
+    if out is None:
+        if x.dtype == tdt:
+            return x
+        out = empty_field(x.shape[0], x.shape[1], tdt, x.device, zero=False)
+    nx, ny = x.shape
+    _lib.call("mg_cast", x.data_ptr(), out.data_ptr(), nx, ny, ld(x), ld(out), code(x.dtype), code(out.dtype),
+              stream_ptr())
+    return out
+
+
+def axpy_(alpha: float, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    _check_same_shape(x, y, "axpy")
+    nx, ny = x.shape
+    _lib.call("mg_axpy", float(alpha), x.data_ptr(), y.data_ptr(), nx, ny, ld(x), ld(y), code(x.dtype),
+              code(y.dtype), stream_ptr())
+    return y
+
+
+def fill_sinsin_(f: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float = 1.0, kx: float = 1.0,
+                 ky: float = 1.0) -> torch.Tensor:
+    nx, ny = f.shape
+    _lib.call("mg_fill_sinsin", f.data_ptr(), nx, ny, ld(f), float(domain[0]), float(domain[1]), float(domain[2]),
+              float(domain[3]), float(amplitude), float(kx), float(ky), code(f.dtype), stream_ptr())
+    return f
+
+
+def maxerr_sinsin(u: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float = 1.0, kx: float = 1.0,
+                  ky: float = 1.0) -> float:
+    w = _workspace(u.device)
+    n = w.numel() - 8
+    out = w[n + 7:n + 8]
+    nx, ny = u.shape
+    _lib.call("mg_maxerr_sinsin", u.data_ptr(), nx, ny, ld(u), float(domain[0]), float(domain[1]), float(domain[2]),
+              float(domain[3]), float(amplitude), float(kx), float(ky), code(u.dtype), w.data_ptr(), out.data_ptr(),
+              stream_ptr())
+    return float(out.item())
