@@ -152,6 +152,55 @@ MG_API int mg_maxerr_sinsin(const void* u, int nx, int ny, int64_t ld, double x0
                      double y1, double amplitude, double kx, double ky, int dtype, double* workspace,
                      double* out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused, temporally blocked V/W-cycle passes ("vector path": TMA-staged, 16-byte aligned fields)
+ *
+ * One launch performs, in one pass over HBM and out of place (u_in -> u_out, u_out != u_in):
+ *     [MG_VC_PROLONG: u += bilinear P(coarse_in)]                 (transfer.py:234-267, multigrid.py:329)
+ *     -> `sweeps` (0..2) red-black Gauss-Seidel sweeps            (smoothers.py:175-207)
+ *     -> [MG_VC_RESTRICT: coarse_out = full-weighting R(f - A u)] (laplacian.py:105-124, transfer.py:100-124)
+ *        or [MG_VC_NORM: sumsq_out[0] = sum over all points of (f - A u)^2]  (grid.py:174-187)
+ * so a V(2,2) level costs three passes: smooth+residual+restrict going down, prolong+correct+smooth
+ * (+norm on the finest level) going up  --  the kernels named in BASELINE.json's north star.
+ * Arithmetic uses reciprocal multiplies and FMA: bit-identical to the basic kernels when hx^2, hy^2
+ * are powers of two (n = 2^k+1 on the unit square), within a few ulp otherwise.
+ * ------------------------------------------------------------------------------------------- */
+#define MG_VC_PROLONG 1          /* front stage: add the prolongated coarse correction */
+#define MG_VC_RESTRICT 2         /* back stage: residual + full-weighting restriction into coarse_out */
+#define MG_VC_NORM 4             /* back stage: residual sum of squares into sumsq_out (needs workspace) */
+#define MG_VC_LOADER_CPASYNC 16  /* stage rows with per-lane cp.async instead of TMA */
+#define MG_VC_NO_STORE 32        /* do not write u_out (pure residual passes, sweeps = 0) */
+#define MG_VC_ROWS(r) (((r) & 0xFFF) << 8) /* override rows per tile (0 = auto) */
+
+/* doubles of workspace MG_VC_NORM needs for an (nx, ny) field */
+MG_API int mg_vc_workspace_doubles(int nx, int ny);
+
+MG_API int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
+               double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
+               int64_t ld_f, int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega,
+               double coefficient, int sweeps, int dtype, int flags, void* stream);
+
+/* `sweeps` temporally blocked RB-GS sweeps in one HBM pass (replaces GaussSeidelSmoother(red_black=True)
+ * .smooth, smoothers.py:117-151; SmoothingKernels.red_black_gauss_seidel / block_gauss_seidel_kernel,
+ * gpu/cuda_kernels.py:348-390, 982-1048). */
+MG_API int mg_vc_smooth(const void* u_in, void* u_out, const void* f, int nx, int ny, int64_t ld_in,
+                 int64_t ld_out, int64_t ld_f, double hx, double hy, double omega, int sweeps, int dtype,
+                 int flags, void* stream);
+
+/* coarse_out = R_fw(f - coefficient*lap_h u) without materialising the fine residual (replaces
+ * LaplacianOperator.residual + RestrictionOperator.apply, multigrid.py:294-300; TransferKernels.
+ * compute_residual + .restriction, gpu/cuda_kernels.py:738-828). */
+MG_API int mg_vc_residual_restrict(const void* u, const void* f, void* coarse_out, int nx, int ny, int64_t ld_u,
+                            int64_t ld_f, int64_t ld_co, double hx, double hy, double coefficient,
+                            int dtype, int flags, void* stream);
+
+/* u_out = smooth^sweeps(u_in + P coarse_in) (replaces ProlongationOperator.apply + `u += e` + post-smooth,
+ * multigrid.py:321-335; TransferKernels.prolongation, gpu/cuda_kernels.py:766-792). */
+MG_API int mg_vc_prolong_correct_smooth(const void* u_in, void* u_out, const void* f, const void* coarse_in,
+                                 int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
+                                 int64_t ld_ci, double hx, double hy, double omega, int sweeps, int dtype,
+                                 int flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(RED_THREADS)
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+void reduce_partials_sum(const double* partials, int n, double* out, cudaStream_t st) {
+  final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(partials, n, out);
+}
+
 }  // namespace mg
 
 // ==============================================================================================

@@ -1,0 +1,482 @@
+// libmgb200: the temporally blocked, fused red-black Gauss-Seidel streaming kernel (sm_100a).
+//
+// One kernel template covers the three fused passes of a V/W-cycle level:
+//
+//   [FRONT: u += P e_c]  ->  NU x (red half-sweep, black half-sweep)  ->  [BACK: r = f - A u, then
+//                                                          full-weighting restriction  OR  sum r^2]
+//
+// in ONE pass over HBM: u_in and f are read once, u_out written once (plus 1/4-size coarse
+// traffic).  Out of place (u_in -> u_out), so tiles never race on halos.
+//
+// Decomposition.  Every WARP owns a strip of 128 columns (32 lanes x 4 contiguous elements) and
+// streams down a tile of rows.  The lane keeps a sliding window of rows in REGISTERS; stage s of
+// the 2*NU half-sweeps works on the row loaded s steps ago, so when row i arrives, row i-2NU is
+// final.  North/south neighbours are the lane's own registers, west/east neighbours of the lane's
+// first/last element come from the adjacent lane by one warp shuffle per half-sweep.  Nothing is
+// exchanged between warps: strips overlap by 2H columns (H = 2NU [+2 with a BACK stage]) and the
+// overlap is recomputed (the recomputed loads hit in L2, DRAM traffic stays algorithmic).  Row
+// tiles overlap the same way (H rows of warm-up).
+//
+// Data movement.  Rows are staged global -> shared by TMA (cp.async.bulk.tensor.2d, one elected
+// lane per warp, mbarrier completion) in boxes of RB rows x 128 columns through an NSTAGE ring
+// that is PRIVATE to the warp (no block-level barrier in the main loop).  TMA zero-fills
+// everything outside the (nx, ny) extent, which gives the Dirichlet ring / padding handling for
+// free.  LOADER = 1 swaps TMA for per-lane 16-byte cp.async with zero-fill (same ring).
+// Results leave through 16-byte vector stores straight from registers.
+//
+// Arithmetic.  Multiplications by the precomputed 1/hx^2, 1/hy^2, 1/(2/hx^2+2/hy^2) and FMA
+// contraction replace the reference's divisions.  On grids whose spacings are powers of two
+// (n = 2^k+1 on the unit square: every BASELINE config) all those products are exact, so the
+// results are BIT-IDENTICAL to the strict kernels / the reference; otherwise they differ by a few
+// ulp (bar: 1e-12 relative per application).
+#pragma once
+#include <cuda.h>
+#include "mg_common.cuh"
+
+namespace mg {
+namespace stream {
+
+constexpr int LANE_V = 4;     // elements per lane per row
+constexpr int STRIP = 128;    // columns per warp strip
+constexpr int BACK_NONE = 0, BACK_RESTRICT = 1, BACK_NORM = 2;
+constexpr int LOADER_TMA = 0, LOADER_CPASYNC = 1;
+
+template <int NU, int BACK> struct Geometry {
+  static constexpr int H = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // first owned local column (halo)
+  static constexpr int OWN_LO = H < 4 ? 4 : H;                    // local column 4 is global column g0+4
+  static constexpr int OWN_HI = STRIP - 1 - OWN_LO;
+  static constexpr int STRIDE = OWN_HI - OWN_LO + 1;              // multiple of 4
+  static constexpr int ROW_LEAD = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // rows streamed before the first owned row
+  static constexpr int ROW_TAIL = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // rows streamed after the last owned row
+  static constexpr int WR = 2 * NU + 2 + (BACK != BACK_NONE ? 1 : 0);    // u window (ages 0..WR-1)
+  static constexpr int FR = 2 * NU + 1 + (BACK != BACK_NONE ? 1 : 0);    // f window (ages 0..FR-1)
+};
+
+struct PassParams {
+  const void* u_in;
+  void* u_out;
+  const void* f;
+  const void* coarse_in;   // e_c (FRONT) or null
+  void* coarse_out;        // restricted residual (BACK_RESTRICT) or null
+  double* partials;        // one double per warp (BACK_NORM) or null
+  int nx, ny, nxc, nyc;
+  int64_t ld_in, ld_out, ld_f, ld_ci, ld_co;
+  int rows_per_tile;       // R (even)
+  int nstrips;
+  int store_u;             // 0: do not write u_out (pure residual passes)
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <typename T> __device__ __forceinline__ T shfl_dn1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
+
+// 4 contiguous elements  <->  shared / global memory
+template <typename T> struct Row4 { T v[4]; };
+
+__device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void lds4(const double* p, double (&v)[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ void stg4(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void stg4(double* p, const double (&v)[4]) {
+  *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+  *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+__device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void ldg2(const float* p, float& a, float& b) {
+  const float2 t = __ldg(reinterpret_cast<const float2*>(p));
+  a = t.x; b = t.y;
+}
+__device__ __forceinline__ void ldg2(const double* p, double& a, double& b) {
+  const double2 t = __ldg(reinterpret_cast<const double2*>(p));
+  a = t.x; b = t.y;
+}
+
+// Fast arithmetic (reciprocal multiplies + FMA); see the header comment for exactness.
+template <typename T>
+__device__ __forceinline__ T relax_fast(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
+  const T nb = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
+  const T unew = (rhs + nb) * s.inv_neg_diag;
+  return fma(s.one_minus_omega, uc, s.omega * unew);
+}
+template <typename T>
+__device__ __forceinline__ T residual_fast(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
+  T t = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
+  t = fma(-uc, s.cc, t);
+  return fma(-s.coeff, t, f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, int NU, bool PROLONG, int BACK, int LOADER, int WARPS, int NSTAGE, int RB>
+__global__ void __launch_bounds__(WARPS * 32)
+    rbgs_stream_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_f,
+                       const PassParams p, const StencilScalars<T> sc) {
+  using G = Geometry<NU, BACK>;
+  static_assert(RB % 2 == 0, "row parity must be static inside a box");
+  constexpr int WR = G::WR, FR = G::FR;
+  constexpr uint32_t ROW_BYTES = STRIP * sizeof(T);
+  constexpr uint32_t BOX_BYTES = RB * ROW_BYTES;  // one array, one stage
+
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full_bar[WARPS][NSTAGE];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * WARPS + warp;
+  // ring of this warp: [stage][array(u,f)][RB][STRIP]
+  unsigned char* ring = smem + (size_t)warp * NSTAGE * 2 * BOX_BYTES;
+
+  if (LOADER == LOADER_TMA) {
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NSTAGE; ++s) mbar_init(&full_bar[warp][s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  if (strip >= p.nstrips) {  // warp-uniform; warps never synchronise with each other
+    if (BACK == BACK_NORM && lane == 0) p.partials[(size_t)blockIdx.y * (gridDim.x * WARPS) + strip] = 0.0;
+    return;
+  }
+
+  const int nx = p.nx, ny = p.ny;
+  const int g0 = strip * G::STRIDE - 4;  // global column of local column 0 (multiple of 4)
+  const int jbase = g0 + lane * LANE_V;  // global column of this lane's element 0
+  const int I0 = blockIdx.y * p.rows_per_tile;
+  const int I1 = min(I0 + p.rows_per_tile, nx);                                    // owned rows [I0, I1)
+  const int i_begin = I0 - G::ROW_LEAD;                                            // even
+  const int i_last = min(I0 + p.rows_per_tile, nx) - 1 + G::ROW_TAIL;
+  const int nbox = (i_last - i_begin + 1 + RB - 1) / RB;
+
+  // per-element masks
+  uint32_t upd = 0, dom = 0, own = 0;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int j = jbase + e, x = lane * LANE_V + e;
+    const bool d = (j >= 0 && j < ny);
+    const bool o = d && x <= G::OWN_HI && (x >= G::OWN_LO || (strip == 0 && x >= 4));
+    upd |= (j >= 1 && j <= ny - 2) ? (1u << e) : 0u;
+    dom |= d ? (1u << e) : 0u;
+    own |= o ? (1u << e) : 0u;
+  }
+
+  // ---- loader ----------------------------------------------------------------------------------
+  auto issue_box = [&](int box) {
+    const int stage = box % NSTAGE;
+    unsigned char* dst_u = ring + (size_t)stage * 2 * BOX_BYTES;
+    unsigned char* dst_f = dst_u + BOX_BYTES;
+    const int row0 = i_begin + box * RB;
+    if (LOADER == LOADER_TMA) {
+      if (lane == 0) {
+        mbar_expect_tx(&full_bar[warp][stage], 2 * BOX_BYTES);
+        tma_load_2d(dst_u, &map_u, g0, row0, &full_bar[warp][stage]);
+        tma_load_2d(dst_f, &map_f, g0, row0, &full_bar[warp][stage]);
+      }
+    } else {
+      // per lane: its own 4 elements of every row of the box; zero-fill outside the domain
+      int nvalid = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) nvalid += (jbase + e >= 0 && jbase + e < ny) ? 1 : 0;  // valid run starts at e=0 or is empty
+      const bool colok = (jbase >= 0) && nvalid > 0;
+      const int jc = colok ? jbase : 0;
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + r;
+        const bool ok = colok && row >= 0 && row < nx;
+        const int rc = ok ? row : 0;
+        const int bytes = ok ? nvalid * (int)sizeof(T) : 0;
+        const T* su = reinterpret_cast<const T*>(p.u_in) + (int64_t)rc * p.ld_in + jc;
+        const T* sf = reinterpret_cast<const T*>(p.f) + (int64_t)rc * p.ld_f + jc;
+        unsigned char* du = dst_u + r * ROW_BYTES + lane * LANE_V * sizeof(T);
+        unsigned char* df = dst_f + r * ROW_BYTES + lane * LANE_V * sizeof(T);
+        if (sizeof(T) == 4) {
+          cp_async16(du, su, bytes);
+          cp_async16(df, sf, bytes);
+        } else {
+          cp_async16(du, su, min(bytes, 16));
+          cp_async16(du + 16, su + 2, max(bytes - 16, 0));
+          cp_async16(df, sf, min(bytes, 16));
+          cp_async16(df + 16, sf + 2, max(bytes - 16, 0));
+        }
+      }
+    }
+  };
+
+  // prologue: fill the ring
+#pragma unroll
+  for (int b = 0; b < NSTAGE; ++b) {
+    if (b < nbox) issue_box(b);
+    if (LOADER == LOADER_CPASYNC) cp_async_commit();  // one group per slot, even when empty
+  }
+
+  // ---- state -----------------------------------------------------------------------------------
+  T w[WR][4];   // w[a] = row loaded a steps ago (age a)
+  T fr[FR][4];  // matching right-hand sides
+#pragma unroll
+  for (int a = 0; a < WR; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) w[a][e] = (T)0;
+#pragma unroll
+  for (int a = 0; a < FR; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) fr[a][e] = (T)0;
+  T rr[3][4];  // residual rows (BACK_RESTRICT): rr[0] newest
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) rr[a][e] = (T)0;
+  double acc = 0.0;  // BACK_NORM
+
+  // coarse correction rows (FRONT): c0 = coarse row floor(i/2), c1 = the next one; 3 columns each
+  T c0[3] = {(T)0, (T)0, (T)0}, c1[3] = {(T)0, (T)0, (T)0};
+  const int jc0 = (g0 >> 1) + 2 * lane;  // coarse column of element 0 (g0 is a multiple of 4, may be -4)
+  auto load_coarse_row = [&](int ic, T(&c)[3]) {
+    T a = (T)0, b = (T)0, d = (T)0;
+    if (ic >= 0 && ic < p.nxc) {
+      const T* row = reinterpret_cast<const T*>(p.coarse_in) + (int64_t)ic * p.ld_ci;
+      if (jc0 >= 0 && jc0 + 1 < p.nyc) {
+        ldg2(row + jc0, a, b);
+      } else {
+        if (jc0 >= 0 && jc0 < p.nyc) a = __ldg(row + jc0);
+        if (jc0 + 1 >= 0 && jc0 + 1 < p.nyc) b = __ldg(row + jc0 + 1);
+      }
+      if (lane == 31 && jc0 + 2 >= 0 && jc0 + 2 < p.nyc) d = __ldg(row + jc0 + 2);
+    }
+    const T nxt = shfl_dn1(a);
+    c[0] = a; c[1] = b; c[2] = (lane == 31) ? d : nxt;
+  };
+  if (PROLONG) {
+    load_coarse_row(i_begin >> 1, c0);  // i_begin is even; >> floors for negatives
+    load_coarse_row((i_begin >> 1) + 1, c1);
+  }
+
+  T* const uout = reinterpret_cast<T*>(p.u_out);
+  T* const cout = reinterpret_cast<T*>(p.coarse_out);
+
+  // ---- main loop over boxes ----------------------------------------------------------------------
+  for (int box = 0; box < nbox; ++box) {
+    const int stage = box % NSTAGE;
+    if (LOADER == LOADER_TMA) {
+      mbar_wait(&full_bar[warp][stage], (uint32_t)((box / NSTAGE) & 1));
+    } else {
+      cp_async_wait<NSTAGE - 1>();
+      __syncwarp();
+    }
+    const T* su = reinterpret_cast<const T*>(ring + (size_t)stage * 2 * BOX_BYTES) + lane * LANE_V;
+    const T* sf = su + RB * STRIP;
+
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const int i = i_begin + box * RB + k;  // newest row; parity of i == parity of k
+      const int kpar = k & 1;
+
+      // (0) shift the windows by one row
+#pragma unroll
+      for (int a = WR - 1; a > 0; --a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[a][e] = w[a - 1][e];
+#pragma unroll
+      for (int a = FR - 1; a > 0; --a)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) fr[a][e] = fr[a - 1][e];
+
+      // (1) newest row from the ring
+      lds4(su + k * STRIP, w[0]);
+      lds4(sf + k * STRIP, fr[0]);
+
+      // (1b) FRONT: u += bilinear prolongation of the coarse correction (transfer.py:234-267 semantics)
+      if (PROLONG) {
+        if (i >= 0 && i < nx) {
+          T add[4];
+          if (kpar == 0) {  // even fine row: coarse row i/2
+            const bool last = (i == nx - 1);
+            add[0] = c0[0];
+            add[2] = c0[1];
+            add[1] = last ? (T)0 : (T)0.5 * (c0[0] + c0[1]);
+            add[3] = last ? (T)0 : (T)0.5 * (c0[1] + c0[2]);
+          } else {  // odd fine row: coarse rows (i-1)/2 and (i+1)/2
+            add[0] = (jbase == ny - 1) ? (T)0 : (T)0.5 * (c0[0] + c1[0]);
+            add[2] = (jbase + 2 == ny - 1) ? (T)0 : (T)0.5 * (c0[1] + c1[1]);
+            add[1] = (T)0.25 * (((c0[0] + c0[1]) + c1[0]) + c1[1]);
+            add[3] = (T)0.25 * (((c0[1] + c0[2]) + c1[1]) + c1[2]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[0][e] = ((dom >> e) & 1u) ? w[0][e] + add[e] : w[0][e];
+        }
+        if (kpar == 1) {  // moving to the next coarse row pair
+#pragma unroll
+          for (int e = 0; e < 3; ++e) c0[e] = c1[e];
+          load_coarse_row(((i + 1) >> 1) + 1, c1);
+        }
+      }
+
+      // (2) the 2*NU half-sweeps, stage s on the row of age s
+#pragma unroll
+      for (int s = 1; s <= 2 * NU; ++s) {
+        const int q = i - s;
+        if (q >= 1 && q <= nx - 2) {  // warp-uniform
+          // colour of stage s is (s-1)&1 (red = (row+col) even first); col parity == element parity
+          const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element (0 or 1), compile-time after unrolling
+          if (e0 == 0) {
+            const T lfx = shfl_up1(w[s][3]);
+            const T n0 = relax_fast<T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
+            const T n2 = relax_fast<T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
+            w[s][0] = (upd & 1u) ? n0 : w[s][0];
+            w[s][2] = (upd & 4u) ? n2 : w[s][2];
+          } else {
+            const T rtx = shfl_dn1(w[s][0]);
+            const T n1 = relax_fast<T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
+            const T n3 = relax_fast<T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
+            w[s][1] = (upd & 2u) ? n1 : w[s][1];
+            w[s][3] = (upd & 8u) ? n3 : w[s][3];
+          }
+        }
+      }
+
+      // (3) the row of age 2NU is final: store the owned part
+      {
+        const int qf = i - 2 * NU;
+        if (p.store_u && qf >= I0 && qf < I1 && qf < nx && own != 0u) {
+          T* dst = uout + (int64_t)qf * p.ld_out + jbase;
+          if (own == 0xFu) {
+            stg4(dst, w[2 * NU]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((own >> e) & 1u) dst[e] = w[2 * NU][e];
+          }
+        }
+      }
+
+      // (4) BACK: residual of the row of age 2NU+1 (its neighbours are final)
+      if (BACK != BACK_NONE) {
+        constexpr int A = 2 * NU + 1;
+        const int q2 = i - A;
+        T r[4] = {(T)0, (T)0, (T)0, (T)0};
+        if (q2 >= 0 && q2 < nx) {
+          if (q2 >= 1 && q2 <= nx - 2) {
+            const T lfx = shfl_up1(w[A][3]);
+            const T rtx = shfl_dn1(w[A][0]);
+            const T r0 = residual_fast<T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
+            const T r1 = residual_fast<T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
+            const T r2 = residual_fast<T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
+            const T r3 = residual_fast<T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
+            r[0] = (upd & 1u) ? r0 : fr[A][0];
+            r[1] = (upd & 2u) ? r1 : fr[A][1];
+            r[2] = (upd & 4u) ? r2 : fr[A][2];
+            r[3] = (upd & 8u) ? r3 : fr[A][3];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) r[e] = fr[A][e];  // boundary rows: r = f (laplacian.py:64,117)
+          }
+        }
+        if (BACK == BACK_NORM) {
+          if (q2 >= I0 && q2 < I1 && q2 < nx) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const T sq = r[e] * r[e];  // squared in T like NumPy's field**2, accumulated in fp64
+              acc += ((own >> e) & 1u) ? (double)sq : 0.0;
+            }
+          }
+        } else {  // BACK_RESTRICT
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            rr[2][e] = rr[1][e];
+            rr[1][e] = rr[0][e];
+            rr[0][e] = r[e];
+          }
+          if (kpar == 0) {  // q2 = i - 2NU - 1 is odd: rows q2-2, q2-1 (centre, even), q2 are complete
+            const int fi = q2 - 1;  // fine centre row
+            const int ic = fi >> 1;
+            if (fi >= I0 && fi < I1 && fi >= 0 && ic < p.nxc) {  // owned coarse row (warp-uniform)
+              const T l2 = shfl_up1(rr[2][3]), l1 = shfl_up1(rr[1][3]), l0 = shfl_up1(rr[0][3]);
+              const bool brow = (ic == 0 || ic == p.nxc - 1);
+              // element 0 -> coarse column jc0, element 2 -> coarse column jc0 + 1
+              T v0, v1;
+              {
+                const T corners = ((l2 + rr[2][1]) + l0) + rr[0][1];
+                const T edges = ((rr[2][0] + rr[0][0]) + l1) + rr[1][1];
+                v0 = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * rr[1][0];
+                const bool b = brow || jc0 == 0 || jc0 == p.nyc - 1;
+                v0 = b ? rr[1][0] : v0;
+              }
+              {
+                const T corners = ((rr[2][1] + rr[2][3]) + rr[0][1]) + rr[0][3];
+                const T edges = ((rr[2][2] + rr[0][2]) + rr[1][1]) + rr[1][3];
+                v1 = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * rr[1][2];
+                const bool b = brow || jc0 + 1 == 0 || jc0 + 1 == p.nyc - 1;
+                v1 = b ? rr[1][2] : v1;
+              }
+              const bool o0 = (own & 1u) != 0u, o1 = (own & 4u) != 0u;
+              T* dst = cout + (int64_t)ic * p.ld_co + jc0;
+              if (o0 && o1) {
+                stg2(dst, v0, v1);
+              } else {
+                if (o0) dst[0] = v0;
+                if (o1) dst[1] = v1;
+              }
+            }
+          }
+        }
+      }
+    }  // rows of the box
+
+    // refill this stage with box + NSTAGE
+    __syncwarp();
+    if (box + NSTAGE < nbox) issue_box(box + NSTAGE);
+    if (LOADER == LOADER_CPASYNC) cp_async_commit();
+  }
+
+  if (BACK == BACK_NORM) {
+    acc = warp_sum(acc);
+    if (lane == 0) p.partials[(size_t)blockIdx.y * (gridDim.x * WARPS) + strip] = acc;
+  }
+}
+
+}  // namespace stream
+}  // namespace mg

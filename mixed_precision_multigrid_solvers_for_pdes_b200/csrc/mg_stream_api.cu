@@ -1,0 +1,173 @@
+// libmgb200: C ABI of the fused / temporally blocked V-cycle passes (mg_vc_* family).
+#include <cudaTypedefs.h>
+#include "mg_stream.cuh"
+
+namespace mg {
+namespace stream {
+int launch_pass_f32_tma(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
+                        const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f32_cpa(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
+                        const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_tma(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
+                        const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f64_cpa(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
+                        const StencilScalars<double>&, cudaStream_t);
+
+constexpr int WARPS = 4;
+constexpr int RB = 4;
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// (nx, ny) row-major field with pitch ld  ->  2-D tiled map, box = RB rows x 128 columns, zero OOB fill
+static int make_map(CUtensorMap* m, const void* base, int nx, int ny, int64_t ld, int dtype) {
+  auto enc = get_encode();
+  if (!enc) return MG_ERR_UNSUPPORTED;
+  const size_t esz = dtype == MG_F64 ? 8 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)ny, (cuuint64_t)nx};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {(cuuint32_t)STRIP, (cuuint32_t)RB};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, dtype == MG_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? MG_OK : MG_ERR_BADARG;
+}
+
+static inline int strip_stride(int nu, int back) {
+  const int h = 2 * nu + (back ? 2 : 0);
+  const int lo = h < 4 ? 4 : h;
+  return STRIP - 2 * lo;
+}
+static inline int num_strips(int ny, int nu, int back) {
+  const int h = 2 * nu + (back ? 2 : 0);
+  const int lo = h < 4 ? 4 : h, hi = STRIP - 1 - lo, stride = hi - lo + 1;
+  // strip k owns global columns up to stride*k - 4 + hi
+  int k = 0;
+  while ((int64_t)stride * k - 4 + hi < ny - 1) ++k;
+  return k + 1;
+}
+static inline int pick_rows(int nx, int nstrips, int override_rows) {
+  if (override_rows > 0) return (override_rows + 1) & ~1;
+  const int target = sm_count() * 12;  // warps we would like in flight
+  int r = 512;
+  while (r > 32 && (int64_t)nstrips * ((nx + r - 1) / r) < target) r >>= 1;
+  return r;
+}
+
+}  // namespace stream
+}  // namespace mg
+
+using namespace mg;
+using namespace mg::stream;
+
+extern "C" {
+
+int mg_vc_workspace_doubles(int nx, int ny) {
+  if (nx < 3 || ny < 3) return 0;
+  const int nstrips = num_strips(ny, 0, 1) + WARPS;  // smallest stride => most strips
+  const int ntiles = (nx + 31) / 32;
+  return nstrips * ntiles + 8;
+}
+
+int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
+               double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
+               int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega, double coefficient, int sweeps,
+               int dtype, int flags, void* stream) {
+  const bool prolong = (flags & MG_VC_PROLONG) != 0;
+  const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
+  const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
+  const bool store = (flags & MG_VC_NO_STORE) == 0;
+  const int rows_override = (flags >> 8) & 0xFFF;
+  if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
+  if (!u_in || !f || nx < 3 || ny < 3 || ld_in < ny || ld_f < ny || hx <= 0 || hy <= 0) return MG_ERR_BADARG;
+  if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
+  if ((flags & MG_VC_RESTRICT) && (flags & MG_VC_NORM)) return MG_ERR_UNSUPPORTED;
+  if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
+  if (!store && back == BACK_NONE) return MG_ERR_BADARG;
+  if (sweeps == 0 && !prolong && back == BACK_NONE) return MG_ERR_BADARG;
+  const int nxc = (nx - 1) / 2 + 1, nyc = (ny - 1) / 2 + 1;
+  if (prolong || back == BACK_RESTRICT) {
+    if ((nx - 1) % 2 || (ny - 1) % 2) return MG_ERR_BADARG;
+    if (prolong && (!coarse_in || ld_ci < nyc)) return MG_ERR_BADARG;
+    if (back == BACK_RESTRICT && (!coarse_out || ld_co < nyc)) return MG_ERR_BADARG;
+  }
+  if (back == BACK_NORM && (!sumsq_out || !workspace)) return MG_ERR_BADARG;
+  const size_t esz = dtype == MG_F64 ? 8 : 4;
+  const int64_t va = 16 / (int64_t)esz;
+  auto misaligned = [&](const void* p, int64_t ld) { return p && (((uintptr_t)p & 15u) || (ld % va)); };
+  if (misaligned(u_in, ld_in) || misaligned(f, ld_f) || (store && misaligned(u_out, ld_out)) ||
+      (prolong && misaligned(coarse_in, ld_ci)) || (back == BACK_RESTRICT && misaligned(coarse_out, ld_co)))
+    return MG_ERR_ALIGN;
+
+  PassParams p;
+  p.u_in = u_in; p.u_out = u_out; p.f = f; p.coarse_in = coarse_in; p.coarse_out = coarse_out;
+  p.partials = workspace;
+  p.nx = nx; p.ny = ny; p.nxc = nxc; p.nyc = nyc;
+  p.ld_in = ld_in; p.ld_out = ld_out; p.ld_f = ld_f; p.ld_ci = ld_ci; p.ld_co = ld_co;
+  p.nstrips = num_strips(ny, sweeps, back);
+  p.rows_per_tile = pick_rows(nx, p.nstrips, rows_override);
+  p.store_u = store ? 1 : 0;
+
+  CUtensorMap mu, mf;
+  memset(&mu, 0, sizeof(mu));
+  memset(&mf, 0, sizeof(mf));
+  if (!cpa) {
+    int rc = make_map(&mu, u_in, nx, ny, ld_in, dtype);
+    if (rc != MG_OK) return rc;
+    rc = make_map(&mf, f, nx, ny, ld_f, dtype);
+    if (rc != MG_OK) return rc;
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (dtype == MG_F64) {
+    auto sc = make_scalars<double>(hx, hy, omega, coefficient);
+    rc = cpa ? launch_pass_f64_cpa(sweeps, prolong, back, mu, mf, p, sc, st)
+             : launch_pass_f64_tma(sweeps, prolong, back, mu, mf, p, sc, st);
+  } else {
+    auto sc = make_scalars<float>(hx, hy, omega, coefficient);
+    rc = cpa ? launch_pass_f32_cpa(sweeps, prolong, back, mu, mf, p, sc, st)
+             : launch_pass_f32_tma(sweeps, prolong, back, mu, mf, p, sc, st);
+  }
+  if (rc != MG_OK) return rc;
+  if (back == BACK_NORM) {
+    const int ntiles = (nx + p.rows_per_tile - 1) / p.rows_per_tile;
+    const int n = ((p.nstrips + WARPS - 1) / WARPS) * WARPS * ntiles;
+    reduce_partials_sum(workspace, n, sumsq_out, st);
+  }
+  return check_launch("mg_vc_pass");
+}
+
+int mg_vc_smooth(const void* u_in, void* u_out, const void* f, int nx, int ny, int64_t ld_in, int64_t ld_out,
+                 int64_t ld_f, double hx, double hy, double omega, int sweeps, int dtype, int flags, void* stream) {
+  return mg_vc_pass(u_in, u_out, f, nullptr, nullptr, nullptr, nullptr, nx, ny, ld_in, ld_out, ld_f, 0, 0, hx, hy,
+                    omega, 1.0, sweeps, dtype, flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_NO_STORE),
+                    stream);
+}
+
+int mg_vc_residual_restrict(const void* u, const void* f, void* coarse_out, int nx, int ny, int64_t ld_u,
+                            int64_t ld_f, int64_t ld_co, double hx, double hy, double coefficient, int dtype,
+                            int flags, void* stream) {
+  const int fl = (flags & ~(MG_VC_PROLONG | MG_VC_NORM)) | MG_VC_RESTRICT | MG_VC_NO_STORE;
+  return mg_vc_pass(u, nullptr, f, nullptr, coarse_out, nullptr, nullptr, nx, ny, ld_u, 0, ld_f, 0, ld_co, hx, hy, 1.0,
+                    coefficient, 0, dtype, fl, stream);
+}
+
+int mg_vc_prolong_correct_smooth(const void* u_in, void* u_out, const void* f, const void* coarse_in, int nx, int ny,
+                                 int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_ci, double hx, double hy,
+                                 double omega, int sweeps, int dtype, int flags, void* stream) {
+  const int fl = (flags & ~(MG_VC_RESTRICT | MG_VC_NORM | MG_VC_NO_STORE)) | MG_VC_PROLONG;
+  return mg_vc_pass(u_in, u_out, f, coarse_in, nullptr, nullptr, nullptr, nx, ny, ld_in, ld_out, ld_f, ld_ci, 0, hx,
+                    hy, omega, 1.0, sweeps, dtype, fl, stream);
+}
+
+}  // extern "C"

@@ -174,3 +174,60 @@ def maxerr_sinsin(u: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float
               float(domain[3]), float(amplitude), float(kx), float(ky), code(u.dtype), w.data_ptr(), out.data_ptr(),
               stream_ptr())
     return float(out.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# Fused / temporally blocked passes (mg_vc_* family)
+# ------------------------------------------------------------------------------------------------
+_vc_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _vc_workspace(dev: torch.device, nx: int, ny: int) -> torch.Tensor:
+    need = _lib.call("mg_vc_workspace_doubles", nx, ny)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr())
+    w = _vc_ws.get(key)
+    if w is None or w.numel() < need:
+        w = torch.zeros(need, dtype=torch.float64, device=dev)
+        _vc_ws[key] = w
+    return w
+
+
+def vc_aligned(*fields) -> bool:
+    """True when every field satisfies the vector path's 16-byte base / pitch alignment."""
+    for t in fields:
+        if t is None:
+            continue
+        va = 16 // t.element_size()
+        if t.data_ptr() % 16 or ld(t) % va:
+            return False
+    return True
+
+
+def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
+            sweeps: int = 2, omega: float = 1.0, coefficient: float = -1.0,
+            coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
+            sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0) -> None:
+    """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS sweeps -> [coarse_out = R(f - A u)] or
+    [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored)."""
+    nx, ny = u_in.shape
+    flags = (rows & 0xFFF) << 8
+    if coarse_in is not None:
+        flags |= _lib.VC_PROLONG
+    if coarse_out is not None:
+        flags |= _lib.VC_RESTRICT
+    if sumsq_out is not None:
+        flags |= _lib.VC_NORM
+    if u_out is None:
+        flags |= _lib.VC_NO_STORE
+    if loader == "cp_async":
+        flags |= _lib.VC_LOADER_CPASYNC
+    elif loader != "tma":
+        raise ValueError(f"unknown loader {loader!r}")
+    ws = _vc_workspace(u_in.device, nx, ny) if sumsq_out is not None else None
+    _lib.call("mg_vc_pass", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+              coarse_in.data_ptr() if coarse_in is not None else None,
+              coarse_out.data_ptr() if coarse_out is not None else None,
+              sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
+              nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
+              ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
+              hx, hy, omega, coefficient, sweeps, code(u_in.dtype), flags, stream_ptr())

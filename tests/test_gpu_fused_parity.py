@@ -1,0 +1,152 @@
+"""GPU parity of the fused / temporally blocked passes (mg_vc_pass through the C ABI) against
+the strict basic kernels and the NumPy oracle.
+
+Bar: BIT-EXACT whenever hx^2, hy^2 and 2/hx^2+2/hy^2 are powers of two (SQUARE n = 2^k+1 grids on
+the unit square -- every BASELINE config), because all reciprocal multiplications are then exact;
+<= 1e-13 relative to max|.| otherwise (reciprocal-multiply + FMA vs true division)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from mixed_precision_multigrid_solvers_for_pdes_b200 import Grid, ops  # noqa: E402
+from mixed_precision_multigrid_solvers_for_pdes_b200.device import empty_field, to_device, to_host  # noqa: E402
+
+LOADERS = ["tma", "cp_async"]
+
+
+def _fields(n, m, dt, seed, domain=(0.0, 1.0, 0.0, 1.0)):
+    rng = np.random.default_rng(seed)
+    g = Grid(n, m, domain, dt)
+    u = rng.uniform(-1, 1, (n, m)).astype(dt)
+    f = rng.uniform(-1, 1, (n, m)).astype(dt)
+    return g, u, f
+
+
+def _cmp(got, exp, exact, what, rtol=1e-13):
+    got = to_host(got) if isinstance(got, torch.Tensor) else got
+    assert got.dtype == exp.dtype and got.shape == exp.shape, what
+    if exact:
+        if not np.array_equal(got, exp):
+            d = np.abs(got.astype(np.float64) - exp.astype(np.float64))
+            idx = np.unravel_index(np.argmax(d), d.shape)
+            raise AssertionError(f"{what}: {np.count_nonzero(d)} mismatches, max {d.max():.3e} at {idx}")
+    else:
+        scale = np.max(np.abs(exp))
+        tol = rtol if exp.dtype == np.float64 else 2e-6
+        assert np.max(np.abs(got.astype(np.float64) - exp.astype(np.float64))) <= tol * scale, what
+
+
+# (nx, ny, exact): exact = square power-of-two spacing
+SHAPES = [(129, 129, True), (257, 513, False), (65, 1025, False), (33, 17, False), (5, 5, True), (9, 241, False),
+          (131, 77, False), (1025, 129, False), (513, 513, True)]
+
+
+@pytest.mark.parametrize("loader", LOADERS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,pow2", SHAPES)
+def test_smooth_pass(n, m, pow2, dt, loader):
+    dom = (0.0, 1.0, 0.0, 1.0) if (pow2 or n in (257, 65, 33, 1025)) else (0.0, 1.3, -0.2, 0.9)
+    g, u, f = _fields(n, m, dt, 5)
+    g = Grid(n, m, dom, dt)
+    du, df = to_device(u)[0], to_device(f)[0]
+    for sweeps in (1, 2):
+        for omega in (1.0, 1.15):
+            out = empty_field(n, m, dt)
+            ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=sweeps, omega=omega, loader=loader)
+            exp = O.rbgs_smooth(u, f, g.hx, g.hy, omega, sweeps)
+            _cmp(out, exp, pow2 and omega == 1.0, f"smooth {n}x{m} {dt.__name__} s={sweeps} w={omega} {loader}")
+    assert np.array_equal(to_host(du), u)  # input untouched (out of place)
+
+
+@pytest.mark.parametrize("loader", LOADERS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,pow2", [s for s in SHAPES if s[0] % 2 == 1 and s[1] % 2 == 1 and s[0] >= 5 and s[1] >= 5])
+def test_smooth_residual_restrict_pass(n, m, pow2, dt, loader):
+    dom = (0.0, 1.0, 0.0, 1.0) if (pow2 or n in (257, 65, 33, 1025)) else (0.0, 1.3, -0.2, 0.9)
+    _, u, f = _fields(n, m, dt, 6)
+    g = Grid(n, m, dom, dt)
+    du, df = to_device(u)[0], to_device(f)[0]
+    nc, mc = (n - 1) // 2 + 1, (m - 1) // 2 + 1
+    for sweeps in (0, 1, 2):
+        out = empty_field(n, m, dt)
+        rc = empty_field(nc, mc, dt)
+        rc.fill_(7.0)
+        ops.vc_pass(du, out if sweeps else None, df, g.hx, g.hy, sweeps=sweeps, coefficient=-1.0, coarse_out=rc,
+                    loader=loader)
+        us = O.rbgs_smooth(u, f, g.hx, g.hy, 1.0, sweeps)
+        exp_rc = O.restrict(O.residual(us, f, g.hx, g.hy, -1.0))
+        if sweeps:
+            _cmp(out, us, pow2, f"u after smooth+restrict {n}x{m} s={sweeps} {loader}")
+        _cmp(rc, exp_rc, pow2, f"restricted residual {n}x{m} {dt.__name__} s={sweeps} {loader}")
+
+
+@pytest.mark.parametrize("loader", LOADERS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,pow2", [s for s in SHAPES if s[0] % 2 == 1 and s[1] % 2 == 1 and s[0] >= 5 and s[1] >= 5])
+def test_prolong_correct_smooth_norm_pass(n, m, pow2, dt, loader):
+    dom = (0.0, 1.0, 0.0, 1.0) if (pow2 or n in (257, 65, 33, 1025)) else (0.0, 1.3, -0.2, 0.9)
+    _, u, f = _fields(n, m, dt, 7)
+    g = Grid(n, m, dom, dt)
+    nc, mc = (n - 1) // 2 + 1, (m - 1) // 2 + 1
+    ec = np.random.default_rng(8).uniform(-1, 1, (nc, mc)).astype(dt)  # non-zero boundary on purpose
+    du, df, dec = to_device(u)[0], to_device(f)[0], to_device(ec)[0]
+    for sweeps in (0, 1, 2):
+        out = empty_field(n, m, dt)
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=sweeps, coarse_in=dec, sumsq_out=ss, loader=loader)
+        uc = u + O.prolong(ec)
+        us = O.rbgs_smooth(uc, f, g.hx, g.hy, 1.0, sweeps)
+        _cmp(out, us, pow2, f"prolong+correct+smooth {n}x{m} {dt.__name__} s={sweeps} {loader}")
+        r = O.residual(us, f, g.hx, g.hy, -1.0)
+        exp_ss = float(np.sum(r.astype(np.float64) ** 2))
+        assert abs(ss.item() - exp_ss) <= (1e-12 if dt is np.float64 else 1e-5) * exp_ss
+        out2 = empty_field(n, m, dt)
+        ops.vc_pass(du, out2, df, g.hx, g.hy, sweeps=sweeps, coarse_in=dec, loader=loader)  # without the norm stage
+        assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("rows", [32, 64, 128])
+def test_tile_height_does_not_change_results(rows):
+    n = 513
+    g, u, f = _fields(n, n, np.float64, 9)
+    du, df = to_device(u)[0], to_device(f)[0]
+    ref = empty_field(n, n, np.float64)
+    ops.vc_pass(du, ref, df, g.hx, g.hy, sweeps=2)
+    out = empty_field(n, n, np.float64)
+    rc = empty_field(257, 257, np.float64)
+    ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=2, coarse_out=rc, rows=rows)
+    assert torch.equal(out, ref)
+    _cmp(rc, O.restrict(O.residual(to_host(ref), f, g.hx, g.hy, -1.0)), True, "restrict rows override")
+
+
+def test_alignment_is_checked():
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MGLibraryError
+    t = torch.zeros(33 * 40 + 1, dtype=torch.float64, device="cuda")[1:].view(33, 40)[:, :33]  # 8-byte offset base
+    a = empty_field(33, 33, np.float64)
+    with pytest.raises(MGLibraryError, match="align"):
+        ops.vc_pass(t, a, a, 0.1, 0.1)
+    with pytest.raises(MGLibraryError):
+        ops.vc_pass(a, a, a, 0.1, 0.1)  # in place is not allowed
+
+
+def test_large_grid_against_basic_kernels():
+    """4097^2 (too slow for the loop reference): fused passes == strict basic kernels, bit for bit."""
+    n = 4097
+    g = Grid(n, n)
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for dt in (torch.float64, torch.float32):
+        u = empty_field(n, n, dt)
+        f = empty_field(n, n, dt)
+        u.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        f.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        out = empty_field(n, n, dt)
+        rc = empty_field(2049, 2049, dt)
+        ops.vc_pass(u, out, f, g.hx, g.hy, sweeps=2, coarse_out=rc)
+        ref = u.clone()
+        ops.smooth_rbgs_(ref, f, g.hx, g.hy, 1.0, 2)
+        assert torch.equal(out, ref)
+        assert torch.equal(rc, ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0)))
