@@ -47,13 +47,16 @@ class _Level:
 class CycleEngine:
     def __init__(self, grids: Sequence, *, smoother, coarse_solver, operators: Sequence, restriction_ops: Sequence,
                  prolongation_ops: Sequence, cycle_type: str = "V", pre: int = 2, post: int = 2,
-                 kernels: str = "auto", device=None):
+                 kernels: str = "auto", loader: str = "tma", device=None):
         self.dev = require_cuda(device)
         self.levels: List[_Level] = [_Level(g, self.dev) for g in grids]
         self.smoother, self.coarse_solver = smoother, coarse_solver
         self.operators, self.restriction_ops, self.prolongation_ops = list(operators), list(restriction_ops), list(prolongation_ops)
         self.cycle_type, self.pre, self.post = cycle_type, pre, post
+        if kernels not in ("auto", "basic", "fused"):
+            raise ValueError(f"kernels must be 'auto', 'basic' or 'fused', got {kernels!r}")
         self.kernels = kernels
+        self.loader = loader
         self.coarse_info = torch.zeros(2, dtype=torch.float64, device=self.dev)
 
     # -- per-level building blocks ----------------------------------------------------------------
@@ -93,14 +96,79 @@ class CycleEngine:
             sol, _ = cs.solve(g, op, b.f, b.u, precision_manager)
             b.u.copy_(sol)
 
+    # -- fused path ---------------------------------------------------------------------------------
+    def _fusable(self, lvl: int, level_dtypes: Sequence) -> bool:
+        """The fused passes implement: red-black GS, LaplacianOperator, full weighting, bilinear,
+        equal dtypes on both levels, 16-byte aligned pitched buffers (ours always are)."""
+        if self.kernels == "basic":
+            return False
+        op = self.operators[lvl]
+        ok = (getattr(self.smoother, "kind", None) == "rbgs" and type(op).__name__ == "LaplacianOperator"
+              and getattr(self.restriction_ops[lvl], "method", None) == "full_weighting"
+              and getattr(self.prolongation_ops[lvl], "method", None) == "bilinear"
+              and torch_dtype(level_dtypes[lvl]) == torch_dtype(level_dtypes[lvl + 1]))
+        if not ok and self.kernels == "fused":
+            raise ValueError("kernels='fused' needs GaussSeidelSmoother(red_black=True), LaplacianOperator, "
+                             "full_weighting restriction, bilinear prolongation and one dtype per level pair")
+        return ok
+
+    def _reps(self, lvl: int) -> int:
+        L = self.num_levels
+        if self.cycle_type == "V":
+            return 1
+        if self.cycle_type == "W":
+            return 2
+        if self.cycle_type == "F":
+            return max(1, 2 ** (L - lvl - 2))
+        return 0  # reference: unknown cycle strings fall through all branches (multigrid.py:309-319)
+
+    def _cycle_fused(self, level_dtypes, lvl, precision_manager, sumsq_out) -> None:
+        g = self.levels[lvl].grid
+        b = self.levels[lvl].bufs(level_dtypes[lvl])
+        c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
+        coeff, omega, ld = self.operators[lvl].coefficient, self.smoother.omega, self.loader
+        # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
+        n = self.pre
+        while n > 2:
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld)
+            b.u, b.tmp = b.tmp, b.u
+            n -= 2
+        if n > 0:
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld)
+            b.u, b.tmp = b.tmp, b.u
+        else:
+            ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld)
+        c.u.zero_()
+        for _ in range(self._reps(lvl)):
+            self.cycle(level_dtypes, lvl + 1, precision_manager)
+        # up: prolongation + correction fused into the first post-smoothing pass, norm into the last
+        n = self.post
+        first = min(n, 2)
+        last = (n - first) == 0
+        ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, omega=omega, coefficient=coeff, coarse_in=c.u,
+                    sumsq_out=sumsq_out if last else None, loader=ld)
+        b.u, b.tmp = b.tmp, b.u
+        n -= first
+        while n > 0:
+            k = min(n, 2)
+            n -= k
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, omega=omega, coefficient=coeff,
+                        sumsq_out=sumsq_out if n == 0 else None, loader=ld)
+            b.u, b.tmp = b.tmp, b.u
+
     # -- the recursion ------------------------------------------------------------------------------
-    def cycle(self, level_dtypes: Sequence, lvl: int = 0, precision_manager=None) -> None:
-        """One cycle on level `lvl`, in place on that level's ``u`` for ``level_dtypes[lvl]``."""
+    def cycle(self, level_dtypes: Sequence, lvl: int = 0, precision_manager=None, sumsq_out=None) -> bool:
+        """One cycle on level `lvl`, updating that level's ``u`` for ``level_dtypes[lvl]``.
+        With ``sumsq_out`` (1 float64 on the device) the fused path also leaves sum((f - A u)^2) of the
+        final iterate there; returns True when it did."""
         L = self.num_levels
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         if lvl == L - 1:
             self._coarse_solve(lvl, b, precision_manager)
-            return
+            return False
+        if self._fusable(lvl, level_dtypes):
+            self._cycle_fused(level_dtypes, lvl, precision_manager, sumsq_out)
+            return sumsq_out is not None
         if self.pre > 0:
             self._smooth(lvl, b, self.pre)
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
@@ -108,20 +176,13 @@ class CycleEngine:
         rop = self.restriction_ops[lvl]
         ops.restrict(r, getattr(rop, "method", "full_weighting"), out=c.f)
         c.u.zero_()
-        if self.cycle_type == "V":
-            reps = 1
-        elif self.cycle_type == "W":
-            reps = 2
-        elif self.cycle_type == "F":
-            reps = max(1, 2 ** (L - lvl - 2))
-        else:
-            reps = 0  # reference: unknown cycle strings fall through all branches (multigrid.py:309-319)
-        for _ in range(reps):
+        for _ in range(self._reps(lvl)):
             self.cycle(level_dtypes, lvl + 1, precision_manager)
         pop = self.prolongation_ops[lvl]
         ops.prolong(c.u, getattr(pop, "method", "bilinear"), out=b.u, add=True)
         if self.post > 0:
             self._smooth(lvl, b, self.post)
+        return False
 
     def residual_sumsq_async(self, dtype, slot: int = 0) -> torch.Tensor:
         """Launch r = f - A u on level 0 and its sum of squares; returns a device scalar view."""

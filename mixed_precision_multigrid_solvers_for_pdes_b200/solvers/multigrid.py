@@ -34,12 +34,13 @@ class MultigridSolver(BaseSolver):
     def __init__(self, max_levels: int = 4, max_iterations: int = 50, tolerance: float = 1e-8,
                  cycle_type: str = MultigridCycle.V_CYCLE, pre_smooth_iterations: int = 2,
                  post_smooth_iterations: int = 2, coarse_tolerance: float = 1e-12,
-                 coarse_max_iterations: int = 1000, verbose: bool = False, kernels: str = "auto", device=None):
+                 coarse_max_iterations: int = 1000, verbose: bool = False, kernels: str = "auto", loader: str = "tma",
+                 device=None):
         super().__init__(max_iterations, tolerance, verbose, "Multigrid")
         self.max_levels, self.cycle_type = max_levels, cycle_type
         self.pre_smooth_iterations, self.post_smooth_iterations = pre_smooth_iterations, post_smooth_iterations
         self.coarse_tolerance, self.coarse_max_iterations = coarse_tolerance, coarse_max_iterations
-        self.kernels, self.device = kernels, device
+        self.kernels, self.loader, self.device = kernels, loader, device
         self.grids: List = []
         self.operators: List = []
         self.restriction_ops: List = []
@@ -79,7 +80,8 @@ class MultigridSolver(BaseSolver):
                                   operators=self.operators, restriction_ops=self.restriction_ops,
                                   prolongation_ops=self.prolongation_ops, cycle_type=self.cycle_type,
                                   pre=self.pre_smooth_iterations, post=self.post_smooth_iterations,
-                                  kernels=self.kernels, device=self.device)
+                                  kernels=self.kernels, loader=self.loader, device=self.device)
+        self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.engine.dev)
 
     # -- solve (multigrid.py:184-251) ------------------------------------------------------------------
     def _level_dtypes(self, base_dtype, precision_manager) -> List[torch.dtype]:
@@ -133,8 +135,9 @@ class MultigridSolver(BaseSolver):
                     ops.cast(b_old.u, dts[0], out=b_new.u)
                     b_new.f.copy_(f_in)
                 cur_dtype = dts[0]
-            eng.cycle(dts, 0, precision_manager)
-            residual_norm = float(np.sqrt(hxhy * eng.residual_sumsq_async(cur_dtype).item()))
+            fused_norm = eng.cycle(dts, 0, precision_manager, sumsq_out=self._sumsq)
+            ss = self._sumsq if fused_norm else eng.residual_sumsq_async(cur_dtype)
+            residual_norm = float(np.sqrt(hxhy * ss.item()))
             prec = precision_manager.current_precision.value if precision_manager else "double"
             self.history.record_iteration(residual_norm, time.time() - t0, prec, 0)
             self.log_iteration(iteration, residual_norm)

@@ -1,0 +1,85 @@
+"""Micro-benchmark of the fused passes (CUDA events, L2-exceeding inputs). Not the contract bench."""
+import argparse
+import json
+import sys
+import os
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mixed_precision_multigrid_solvers_for_pdes_b200 import ops  # noqa: E402
+from mixed_precision_multigrid_solvers_for_pdes_b200.device import empty_field  # noqa: E402
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in ev:
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2], ts[0]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=16385)
+    ap.add_argument("--dtypes", default="f32,f64")
+    ap.add_argument("--loaders", default="tma,cp_async")
+    ap.add_argument("--rows", default="0")
+    ap.add_argument("--modes", default="smooth2,smooth1,down2,up2,up2norm,resrestrict")
+    a = ap.parse_args()
+    n = a.n
+    h = 1.0 / (n - 1)
+    nc = (n - 1) // 2 + 1
+    for dn in a.dtypes.split(","):
+        dt = torch.float32 if dn == "f32" else torch.float64
+        w = 4 if dn == "f32" else 8
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        u, f, out = (empty_field(n, n, dt) for _ in range(3))
+        u.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        f.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        ec, rc = empty_field(nc, nc, dt), empty_field(nc, nc, dt)
+        ec.copy_(torch.rand((nc, nc), generator=gen, device="cuda", dtype=dt))
+        ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+        # reference point: plain device copy
+        med, best = timeit(lambda: out.copy_(u))
+        print(json.dumps({"kernel": "torch_copy", "dtype": dn, "n": n, "ms": round(med, 4),
+                          "GBs": round(2 * n * n * w / med / 1e6, 1)}), flush=True)
+        for loader in a.loaders.split(","):
+            for rows in [int(r) for r in a.rows.split(",")]:
+                for mode in a.modes.split(","):
+                    kw = dict(loader=loader, rows=rows)
+                    if mode == "smooth2":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, **kw)), 3 * w, 2
+                    elif mode == "smooth1":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=1, **kw)), 3 * w, 1
+                    elif mode == "down2":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_out=rc, **kw)), 3.25 * w, 2
+                    elif mode == "up2":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, **kw)), 3.25 * w, 2
+                    elif mode == "up2norm":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, sumsq_out=ss, **kw)), 3.25 * w, 2
+                    elif mode == "resrestrict":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, None, f, h, h, sweeps=0, coarse_out=rc, **kw)), 2.25 * w, 0
+                    else:
+                        continue
+                    med, best = timeit(fn)
+                    print(json.dumps({"kernel": mode, "dtype": dn, "loader": loader, "rows": rows, "n": n,
+                                      "ms": round(med, 4), "best_ms": round(best, 4),
+                                      "hbm_GBs": round(byt * n * n / med / 1e6, 1),
+                                      "alg_smoother_GBs": round(3 * w * sw * n * n / med / 1e6, 1)}), flush=True)
+        # baseline: basic (unfused) kernels, 2 sweeps in place
+        med, best = timeit(lambda: ops.smooth_rbgs_(out, f, h, h, 1.0, 2))
+        print(json.dumps({"kernel": "basic_rbgs2", "dtype": dn, "n": n, "ms": round(med, 4),
+                          "alg_smoother_GBs": round(3 * w * 2 * n * n / med / 1e6, 1)}), flush=True)
+        del u, f, out, ec, rc
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
