@@ -7,7 +7,9 @@ from . import ops
 from ._lib import LIB_PATH, MGLibraryError
 from .core import Grid, PrecisionLevel, PrecisionManager
 from .operators import BaseOperator, LaplacianOperator, ProlongationOperator, RestrictionOperator
-from .solvers import (BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
+from .problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
+                       TimeSteppingMethod)
+from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
                       MultigridCycle, MultigridSolver, SymmetricGaussSeidelSmoother, WeightedJacobiSmoother)
 
 __version__ = "0.1.0"
@@ -16,4 +18,6 @@ GPU_AVAILABLE = True  # the only path there is
 __all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "RestrictionOperator",
            "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
            "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
-           "SymmetricGaussSeidelSmoother", "MGLibraryError", "ops", "LIB_PATH"]
+           "SymmetricGaussSeidelSmoother", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",
+           "PoissonProblem", "HeatProblem", "TimeSteppingConfig", "TimeSteppingMethod", "PoissonTestProblems",
+           "HeatTestProblems", "MGLibraryError", "ops", "LIB_PATH"]

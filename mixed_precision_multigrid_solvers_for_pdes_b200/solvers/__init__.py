@@ -1,7 +1,8 @@
 from .base import BaseSolver, ConvergenceHistory, IterativeSolver
+from .mixed_precision import MixedPrecisionMultigrid, MixedPrecisionMultigridSolver
 from .multigrid import MultigridCycle, MultigridSolver
 from .smoothers import (GaussSeidelSmoother, JacobiSmoother, SymmetricGaussSeidelSmoother,
                         WeightedJacobiSmoother)
 
-__all__ = ["BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver", "MultigridCycle",
+__all__ = ["BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver", "MultigridCycle", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",
            "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother", "SymmetricGaussSeidelSmoother"]

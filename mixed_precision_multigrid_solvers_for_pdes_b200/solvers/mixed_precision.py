@@ -1,0 +1,264 @@
+"""``MixedPrecisionMultigrid``: the facade the reference documents but never ships
+(README.md:73-92, docs/sphinx/index.rst:23-36, docs/TROUBLESHOOTING.md:144-253), built on the
+B200 cycle engine.
+
+    solver = MixedPrecisionMultigrid(precision_strategy='adaptive', switch_threshold=1e-6, use_gpu=True)
+    solution, info = solver.solve(problem)
+
+Precision driver (normative spec: docs/methodology.md:325-360; thresholds and names:
+core/precision.py:155-302, applications/mixed_precision_analysis.py:72-105):
+
+  * fp32 phase  --  "fp32 smoothing / fp64 residual" iterative refinement: the iterate u and the
+    right-hand side stay in fp64 in HBM; each cycle computes r = f - A u in fp64, rounds it to fp32,
+    runs one V/W-cycle on A e = r entirely in fp32 (e0 = 0) and adds e to the fp64 iterate.  In exact
+    arithmetic this IS one multigrid cycle on A u = f, so cycle counts match the fp64 reference, and
+    unlike an all-fp32 iterate it can reach discretisation accuracy below fp32 resolution
+    (3e-9 at 16385^2).
+  * switch      --  once ||r|| <= switch_threshold, or the residual stagnates (ratio > 0.95 over the last
+    cycles, precision.py:189-246 / methodology.md:337), the driver continues with fp64 cycles.
+  * strategies  --  'double' (fp64 only: the reference's convergent configuration), 'single' (fp32 only,
+    floors at fp32 resolution), 'adaptive' / 'mixed' / 'conservative' / 'mixed_conservative' (switch at
+    `switch_threshold`, default 1e-6), 'aggressive' / 'mixed_aggressive' (default 1e-4),
+    'refinement' (fp32 cycles all the way; promotion only on stagnation).
+
+The convergence test is the reference's: h-scaled L2 norm of f - A u over all points < tolerance
+(core/grid.py:174-187, solvers/base.py:123-143)."""
+from __future__ import annotations
+
+import time
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..core.grid import Grid
+from ..device import empty_field, like_input, require_cuda, to_device
+from ..operators.laplacian import LaplacianOperator
+from ..operators.transfer import ProlongationOperator, RestrictionOperator
+from .engine import CycleEngine
+from .smoothers import GaussSeidelSmoother, JacobiSmoother
+
+_STRATEGIES = {
+    "double": ("fp64", None), "fp64": ("fp64", None), "float64": ("fp64", None),
+    "single": ("fp32", None), "fp32": ("fp32", None), "float32": ("fp32", None),
+    "adaptive": ("switch", 1e-6), "mixed": ("switch", 1e-6), "conservative": ("switch", 1e-6),
+    "mixed_conservative": ("switch", 1e-6), "aggressive": ("switch", 1e-4), "mixed_aggressive": ("switch", 1e-4),
+    "refinement": ("refine", None),
+}
+
+
+class MixedPrecisionMultigrid:
+    def __init__(self, precision_strategy: str = "adaptive", switch_threshold: Optional[float] = None,
+                 use_gpu: bool = True, max_iterations: int = 50, tolerance: float = 1e-8,
+                 max_levels: Optional[int] = None, cycle_type: str = "V", pre_smooth_iterations: int = 2,
+                 post_smooth_iterations: int = 2, smoother: str = "red_black_gauss_seidel",
+                 damping_factor: float = 1.0, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
+                 stagnation_ratio: float = 0.95, max_grid_size: Optional[int] = None,
+                 gpu_memory_fraction: Optional[float] = None, min_precision: Optional[str] = None,
+                 kernels: str = "auto", loader: str = "tma", device=None, verbose: bool = False):
+        key = str(precision_strategy).lower()
+        if key not in _STRATEGIES:
+            raise ValueError(f"Unknown precision strategy: {precision_strategy}")
+        if not use_gpu:
+            raise ValueError("use_gpu=False is not available: this build has no CPU path (the reference's NumPy "
+                             "solver is the CPU implementation)")
+        self.precision_strategy = key
+        self.mode, default_thr = _STRATEGIES[key]
+        self.switch_threshold = switch_threshold if switch_threshold is not None else (default_thr or 1e-6)
+        if min_precision is not None and str(min_precision).lower() in ("double", "fp64", "float64"):
+            self.mode = "fp64"
+        self.use_gpu, self.max_iterations, self.tolerance = use_gpu, max_iterations, tolerance
+        self.max_levels, self.cycle_type = max_levels, cycle_type
+        self.pre, self.post = pre_smooth_iterations, post_smooth_iterations
+        self.smoother_name, self.damping_factor = smoother, damping_factor
+        self.coarse_tolerance, self.coarse_max_iterations = coarse_tolerance, coarse_max_iterations
+        self.stagnation_ratio = stagnation_ratio
+        self.max_grid_size, self.gpu_memory_fraction = max_grid_size, gpu_memory_fraction
+        self.kernels, self.loader, self.device, self.verbose = kernels, loader, device, verbose
+        self.enable_precision_monitoring = False
+        self.precision_switches: List[Dict[str, Any]] = []
+        self._engine: Optional[CycleEngine] = None
+        self._shape = None
+
+    # -- setup ----------------------------------------------------------------------------------------
+    def _make_smoother(self):
+        n = self.smoother_name.lower()
+        if n in ("red_black_gauss_seidel", "rbgs", "red_black", "gauss_seidel_rb"):
+            return GaussSeidelSmoother(relaxation_parameter=self.damping_factor, red_black=True)
+        if n in ("gauss_seidel", "lexicographic"):
+            return GaussSeidelSmoother(relaxation_parameter=self.damping_factor)
+        if n in ("jacobi", "weighted_jacobi"):
+            return JacobiSmoother(relaxation_parameter=2.0 / 3.0 if self.damping_factor == 1.0 else self.damping_factor)
+        raise ValueError(f"Unknown smoother: {self.smoother_name}")
+
+    def _levels_for(self, nx: int, ny: int) -> int:
+        """Default: coarsen down to the 5x5 floor of the reference hierarchy (multigrid.py:158-160)."""
+        if self.max_levels is not None:
+            return self.max_levels
+        L, a, b = 1, nx, ny
+        while (a - 1) % 2 == 0 and (b - 1) % 2 == 0 and (a - 1) // 2 + 1 >= 5 and (b - 1) // 2 + 1 >= 5:
+            a, b, L = (a - 1) // 2 + 1, (b - 1) // 2 + 1, L + 1
+        return L
+
+    def setup(self, nx: int, ny: int, domain=(0.0, 1.0, 0.0, 1.0)) -> None:
+        if self.max_grid_size is not None and max(nx, ny) > self.max_grid_size:
+            raise ValueError(f"grid {nx}x{ny} exceeds max_grid_size={self.max_grid_size}")
+        dev = require_cuda(self.device)
+        g = Grid(nx, ny, tuple(domain))
+        grids = [g]
+        for _ in range(1, self._levels_for(nx, ny)):
+            try:
+                c = grids[-1].coarsen()
+            except ValueError:
+                break
+            if c.nx < 5 or c.ny < 5:
+                break
+            grids.append(c)
+        op = LaplacianOperator(-1.0)  # the convergent sign convention
+        L = len(grids)
+        self._engine = CycleEngine(
+            grids, smoother=self._make_smoother(),
+            coarse_solver=GaussSeidelSmoother(max_iterations=self.coarse_max_iterations, tolerance=self.coarse_tolerance),
+            operators=[op] * L, restriction_ops=[RestrictionOperator("full_weighting")] * (L - 1),
+            prolongation_ops=[ProlongationOperator("bilinear")] * (L - 1), cycle_type=self.cycle_type, pre=self.pre,
+            post=self.post, kernels=self.kernels, loader=self.loader, device=dev)
+        self._shape, self._domain, self._grid = (nx, ny), tuple(domain), g
+        self._sumsq = torch.zeros(2, dtype=torch.float64, device=dev)
+        # fp64 iterate / rhs of the refinement phase live in the engine's fp64 level-0 buffers
+
+    # -- one cycle in each precision phase -----------------------------------------------------------------
+    def _cycle_fp64(self) -> float:
+        eng = self._engine
+        L = eng.num_levels
+        fused = eng.cycle([torch.float64] * L, 0, None, sumsq_out=self._sumsq[0:1])
+        ss = self._sumsq[0:1] if fused else eng.residual_sumsq_async(torch.float64)
+        return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))
+
+    def _cycle_fp32_only(self) -> float:
+        eng = self._engine
+        L = eng.num_levels
+        fused = eng.cycle([torch.float32] * L, 0, None, sumsq_out=self._sumsq[0:1])
+        ss = self._sumsq[0:1] if fused else eng.residual_sumsq_async(torch.float32)
+        return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))
+
+    def _refinement_residual(self) -> float:
+        """r32 = fp32(f - A u) from the fp64 iterate, and the fp64 h-scaled norm of it."""
+        eng, g = self._engine, self._grid
+        b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)
+        ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp)   # fp64 residual
+        ss = ops.sumsq_async(b64.tmp, slot=1)
+        ops.cast(b64.tmp, torch.float32, out=b32.f)
+        return float(np.sqrt(g.hx * g.hy * ss.item()))
+
+    def _cycle_refinement(self) -> None:
+        """One fp32 cycle on A e = r32 (e0 = 0), then u64 += e32."""
+        eng = self._engine
+        L = eng.num_levels
+        b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)
+        b32.u.zero_()
+        eng.cycle([torch.float32] * L, 0, None)
+        b32 = eng.levels[0].bufs(torch.float32)
+        ops.axpy_(1.0, b32.u, b64.u)
+
+    # -- public API ------------------------------------------------------------------------------------------
+    def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None
+              ) -> Tuple[Any, Dict[str, Any]]:
+        t_start = time.perf_counter()
+        nx = nx or getattr(problem, "nx", None)
+        ny = ny or getattr(problem, "ny", None) or nx
+        rhs = getattr(problem, "rhs_array", None)
+        if nx is None:
+            if rhs is None:
+                raise ValueError("grid size unknown: give PoissonProblem(..., nx=, ny=) or solve(problem, nx=, ny=)")
+            nx, ny = rhs.shape
+        domain = tuple(getattr(problem, "domain", (0.0, 1.0, 0.0, 1.0)))
+        if self._engine is None or self._shape != (nx, ny) or self._domain != domain:
+            self.setup(nx, ny, domain)
+        eng, g = self._engine, self._grid
+        b64 = eng.levels[0].bufs(torch.float64)
+        was_np = True
+        # right-hand side into the fp64 level-0 buffer
+        if rhs is not None:
+            d, was_np = to_device(rhs, device=eng.dev)
+            b64.f.copy_(d)
+        elif getattr(problem, "device_mms", None) is not None:
+            amp, kx, ky = problem.device_mms
+            ops.fill_sinsin_(b64.f, domain, amp, kx, ky)
+        else:
+            f_host = np.asarray(problem.source_function(g.X, g.Y), dtype=np.float64)
+            b64.f.copy_(to_device(f_host, device=eng.dev)[0])
+        if initial_guess is None:
+            b64.u.zero_()
+        else:
+            b64.u.copy_(to_device(initial_guess, device=eng.dev, dtype=torch.float64)[0])
+        t_setup = time.perf_counter() - t_start
+
+        history: List[float] = []
+        precisions: List[str] = []
+        self.precision_switches = []
+        phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
+        if phase == "fp32":
+            b32 = eng.levels[0].bufs(torch.float32)
+            ops.cast(b64.f, torch.float32, out=b32.f)
+            ops.cast(b64.u, torch.float32, out=b32.u)
+        converged = False
+        iteration = 0
+        torch.cuda.synchronize(eng.dev)
+        t_cycles = time.perf_counter()
+        pending = self._refinement_residual() if phase == "refine" else None  # ||r(u_0)||
+        for iteration in range(1, self.max_iterations + 1):
+            if phase == "refine":
+                self._cycle_refinement()
+                norm = self._refinement_residual()  # residual of the new iterate (also next cycle's rhs)
+                precisions.append("mixed")
+            elif phase == "fp64":
+                norm = self._cycle_fp64()
+                precisions.append("float64")
+            else:
+                norm = self._cycle_fp32_only()
+                precisions.append("float32")
+            history.append(norm)
+            if self.verbose:
+                print(f"cycle {iteration}: ||r|| = {norm:.3e} [{precisions[-1]}]")
+            if norm < self.tolerance:
+                converged = True
+                break
+            if phase == "refine":
+                stagnating = (len(history) >= 3 and all(history[-k] > self.stagnation_ratio * history[-k - 1]
+                                                        for k in (1, 2)))
+                if (self.mode == "switch" and norm <= self.switch_threshold) or stagnating:
+                    self.precision_switches.append({"iteration": iteration, "residual": norm, "from": "mixed",
+                                                    "to": "float64",
+                                                    "reason": "stagnation" if stagnating else "switch_threshold"})
+                    phase = "fp64"
+        torch.cuda.synchronize(eng.dev)
+        t_solve = time.perf_counter() - t_cycles
+
+        if phase == "fp32":
+            b32 = eng.levels[0].bufs(torch.float32)
+            u_dev = ops.cast(b32.u, torch.float64, out=b64.tmp)
+        else:
+            u_dev = eng.levels[0].bufs(torch.float64).u
+        solution = like_input(u_dev, True) if was_np else u_dev.clone()
+        total = time.perf_counter() - t_start
+        ratios = [history[k] / history[k - 1] for k in range(max(1, len(history) - 4), len(history))
+                  if history[k - 1] > 0 and 0 < history[k] / history[k - 1] < 1]
+        info = {
+            "converged": converged, "iterations": iteration, "final_residual": history[-1] if history else pending,
+            "residual": history[-1] if history else pending, "residual_history": history,
+            "initial_residual": pending, "convergence_rate": float(np.mean(ratios)) if ratios else 0.0,
+            "solve_time": total, "cycle_time": t_solve, "setup_time": t_setup, "total_time": total,
+            "average_time_per_iteration": t_solve / max(1, iteration), "precision_history": precisions,
+            "precision_levels_used": sorted(set(precisions)), "precision_switches": list(self.precision_switches),
+            "precision_strategy": self.precision_strategy, "switch_threshold": self.switch_threshold,
+            "cycle_type": self.cycle_type, "num_levels": eng.num_levels,
+            "grid_hierarchy": [(l.grid.nx, l.grid.ny) for l in eng.levels], "level_timings": {},
+            "pre_smooth_iterations": self.pre, "post_smooth_iterations": self.post,
+            "unknowns_per_second": nx * ny * iteration / t_solve if t_solve > 0 else 0.0,
+        }
+        return solution, info
+
+
+# doc-only aliases seen in the reference notebooks
+MixedPrecisionMultigridSolver = MixedPrecisionMultigrid

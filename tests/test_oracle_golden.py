@@ -107,3 +107,56 @@ def test_solve_257(solve_golden, golden_meta):
 def test_closed_form_error():
     assert abs(O.mms_discretisation_error(129) - 5.020091592e-5) < 1e-13
     assert abs(O.mms_discretisation_error(16385) - 3.063928466e-9) < 1e-15
+
+
+# ----------------------------------------------------------------------------------------------
+# The plain-C oracle (oracle/mg_oracle.c, OpenMP) against the same golden vectors
+# ----------------------------------------------------------------------------------------------
+from oracle import c_oracle as CO  # noqa: E402
+
+
+def test_c_oracle_ops_bitwise(ops_golden, golden_meta):
+    G = ops_golden
+    for key, nx, ny, dom, dt in _cases(golden_meta):
+        g = O.OGrid(nx, ny, dom, np.dtype(dt).type)
+        u, f, uc = G[f"{key}_u"], G[f"{key}_f"], G[f"{key}_uc"]
+        for coeff in (1.0, -1.0, 2.5):
+            _eq(CO.apply_laplacian(u, g.hx, g.hy, coeff), G[f"{key}_apply_{coeff}"], f"{key} apply {coeff}")
+            _eq(CO.residual(u, f, g.hx, g.hy, coeff), G[f"{key}_residual_{coeff}"], f"{key} residual {coeff}")
+        for omega in (1.0, 1.3):
+            for sweeps in (1, 2, 3):
+                _eq(CO.rbgs_smooth(u, f, g.hx, g.hy, omega, sweeps), G[f"{key}_rbgs_{omega}_{sweeps}"], f"{key} rbgs")
+            _eq(CO.lexgs_smooth(u, f, g.hx, g.hy, omega, 2), G[f"{key}_lexgs_{omega}_2"], f"{key} lexgs")
+        for sweeps in (1, 3):
+            _eq(CO.jacobi_smooth(u, f, g.hx, g.hy, 2.0 / 3.0, sweeps), G[f"{key}_jacobi_{sweeps}"], f"{key} jacobi")
+            _eq(CO.jacobi_smooth(u, f, g.hx, g.hy, 4.0 / 5.0, sweeps), G[f"{key}_wjacobi_{sweeps}"], f"{key} wjacobi")
+        for m in ("full_weighting", "injection", "half_weighting"):
+            _eq(CO.restrict(u, m), G[f"{key}_restrict_{m}"], f"{key} restrict {m}")
+        for m in ("bilinear", "injection"):
+            _eq(CO.prolong(uc, m), G[f"{key}_prolong_{m}"], f"{key} prolong {m}")
+        ref = float(G[f"{key}_l2"])
+        assert abs(CO.l2_norm(f, g.hx, g.hy) - ref) <= (1e-14 if dt == "float64" else 1e-6) * ref
+
+
+def test_c_oracle_solves_match_reference(solve_golden, golden_meta):
+    for m in golden_meta["solves"]:
+        if m["dtype"] != "float64" or m["precision"] is not None:
+            continue
+        s = _solver_for(m)
+        s.ops = CO
+        u, info = s.solve(O.mms_rhs(m["nx"], m["ny"]))
+        assert info["iterations"] == m["iterations"], m["name"]
+        # same arithmetic; np_oracle.l2_norm (NumPy pairwise sum) still drives the stopping tests
+        assert np.array_equal(np.array(info["residual_history"]), solve_golden[f"{m['name']}_hist"]), m["name"]
+        if f"{m['name']}_u" in solve_golden:
+            assert np.array_equal(u, solve_golden[f"{m['name']}_u"]), m["name"]
+
+
+def test_c_oracle_large_grid_matches_numpy_oracle():
+    n = 1025
+    f = O.mms_rhs(n)
+    a = O.OracleMultigrid(n, max_levels=9, max_iterations=2)
+    b = O.OracleMultigrid(n, max_levels=9, max_iterations=2, ops=CO)
+    ua, ia = a.solve(f)
+    ub, ib = b.solve(f)
+    assert np.array_equal(ua, ub) and ia["residual_history"] == ib["residual_history"]
