@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the multigrid V-cycle hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA kernels through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[2], the config the metric's roofline target is quoted on):
+2-D Poisson, 16385 x 16385 unknowns, manufactured f = 2 pi^2 sin(pi x) sin(pi y), u0 = 0,
+mixed-precision V(2,2) red-black Gauss-Seidel: fp64 iterate and residual, fp32 V-cycle correction,
+switch to fp64 cycles at ||r|| <= 1e-6 (precision_strategy='adaptive').
+
+A STEP is one multigrid cycle of the real solve loop, including its convergence test (one 8-byte
+device->host read).  When a solve converges inside the timed region the next one starts from u = 0.
+value = nx*ny*K / time  [fine-grid unknowns/s per V-cycle]  (reference gpu/gpu_benchmark.py:248).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every key."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+def _metric_name():
+    try:
+        return json.load(open(os.path.join(ROOT, "BASELINE.json")))["metric"]
+    except Exception:
+        return "V-cycle fine-grid unknowns/sec + smoother HBM GB/s vs peak at 1/2/4/8 B200"
+
+
+METRIC = _metric_name()
+UNIT = "unknowns/s"
+BYTES_PER_UNKNOWN_FP64_V22 = 90.7  # fused-minimum traffic of one fp64 V(2,2) cycle
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=16385, help="fine grid points per side (per GPU slab height for N>1)")
+    ap.add_argument("--strategy", default="adaptive")
+    ap.add_argument("--cycle", default="V")
+    ap.add_argument("--loader", default="tma")
+    ap.add_argument("--tolerance", type=float, default=None,
+                    help="absolute h-scaled L2 residual tolerance; default 1e-8 (reference) up to 4097^2, 1e-7 above: "
+                         "evaluating f - A u in fp64 has a rounding floor of ~eps*8/h^2*|u| = 3e-8 at h = 1/16384")
+    ap.add_argument("--cpu-n", type=int, default=4097, help="grid of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        try:
+            rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
+            sm = sorted(float(r[1]) for r in rows)
+            out["samples"] = len(rows)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["power_w_max"] = max(float(r[3]) for r in rows)
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                out["reasons"] = [n for k, n in enumerate(names) if any(r[4 + k].strip() == "Active" for r in rows)]
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm on the host cores (oracle port; the reference itself is pure-Python
+# loops at ~6e4 unknowns/s and does not exist on the GPU box)
+# ------------------------------------------------------------------------------------------------------
+def cpu_cycles(n: int, cycles: int, threads_hint=None):
+    """Time `cycles` V(2,2) RB-GS fp64 cycles of the C/OpenMP oracle on an n x n grid.
+    Returns (unknowns_per_s, seconds, threads_used, residual_history)."""
+    import numpy as np
+
+    from oracle import c_oracle as CO
+    from oracle import np_oracle as O
+    L = 1
+    a = n
+    while (a - 1) % 2 == 0 and (a - 1) // 2 + 1 >= 5:
+        a, L = (a - 1) // 2 + 1, L + 1
+    f = O.mms_rhs(n)
+    s = O.OracleMultigrid(n, max_levels=L, max_iterations=cycles, tolerance=0.0, ops=CO)
+    t0 = time.perf_counter()
+    _, info = s.solve(f)
+    dt = time.perf_counter() - t0
+    return n * n * info["iterations"] / dt, dt, CO.num_threads(), info["residual_history"]
+
+
+def pick_cpu_threads():
+    """OpenMP helps only when the cores are really there (containers often expose more CPUs than their
+    quota): time one small cycle with all threads and with one, keep the faster setting."""
+    best = None
+    for th in (os.cpu_count() or 1, 1):
+        code = (f"import os,sys;os.environ['OMP_NUM_THREADS']='{th}';sys.path.insert(0,{ROOT!r});"
+                "import bench;v,dt,t,_=bench.cpu_cycles(1025,1);print(v)")
+        try:
+            v = float(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120).stdout.split()[-1])
+        except Exception:
+            continue
+        if best is None or v > best[1]:
+            best = (th, v)
+    return best[0] if best else 1
+
+
+def run_cpu_baseline(n: int, cycles: int):
+    th = pick_cpu_threads()
+    code = (f"import os,sys,json;os.environ['OMP_NUM_THREADS']='{th}';sys.path.insert(0,{ROOT!r});"
+            f"import bench;v,dt,t,h=bench.cpu_cycles({n},{cycles});print(json.dumps([v,dt,t,h]))")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1800)
+    v, dt, t, hist = json.loads(out.stdout.strip().splitlines()[-1])
+    return {"value": v, "unit": UNIT, "cores": int(t), "kind": "port",
+            "sample": f"{cycles} fp64 V(2,2) red-black GS cycles on {n}x{n} (C/OpenMP restatement of the reference "
+                      f"loops, oracle/mg_oracle.c; {dt:.1f} s; host has {os.cpu_count()} logical CPUs)",
+            "seconds": dt, "final_residual": hist[-1]}
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cyc = max(1, a.steps)
+    base = run_cpu_baseline(a.cpu_n, cyc)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
+            "steps": cyc, "warmup": 0, "ms_per_step": base["seconds"] / cyc * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"2D Poisson V(2,2) RB-GS cycles, fp64, CPU sample {a.cpu_n}x{a.cpu_n} of the "
+                                   f"{a.n}x{a.n} config (unknowns/s is size-independent: O(N) work per cycle)"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------
+def gpu_arm(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MixedPrecisionMultigrid, PoissonProblem, _lib, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = a.n
+    peak, peak_src = load_peaks()
+    tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
+
+    if world > 1:
+        from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import run_distributed_bench
+        line = run_distributed_bench(a, world, rank, dev, peak, peak_src, ClockSampler)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
+
+    solver = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
+                                     cycle_type=a.cycle, loader=a.loader, max_iterations=10 ** 9, device=dev)
+    solver.setup(n, n)
+    eng, g = solver._engine, solver._grid
+    b64 = eng.levels[0].bufs(torch.float64)
+    ops.fill_sinsin_(b64.f, (0.0, 1.0, 0.0, 1.0), 2 * np.pi ** 2, 1.0, 1.0)
+
+    # the solve loop of MixedPrecisionMultigrid.solve, unrolled into steps
+    state = {"phase": None, "hist": [], "solves": 0, "cycles_per_solve": [], "precisions": []}
+
+    def restart():
+        b64.u.zero_()
+        state["phase"] = "refine" if solver.mode in ("switch", "refine") else solver.mode
+        state["hist"] = []
+        if state["phase"] == "refine":
+            solver._refinement_residual()
+        elif state["phase"] == "fp32":
+            b32 = eng.levels[0].bufs(torch.float32)
+            ops.cast(b64.f, torch.float32, out=b32.f)
+            b32.u.zero_()
+
+    def step():
+        ph = state["phase"]
+        if ph == "refine":
+            norm = solver._cycle_refinement()
+        elif ph == "fp64":
+            norm = solver._cycle_fp64()
+        else:
+            norm = solver._cycle_fp32_only()
+        state["hist"].append(norm)
+        state["precisions"].append(ph)
+        if norm < solver.tolerance or len(state["hist"]) >= 30:
+            state["solves"] += 1
+            state["cycles_per_solve"].append(len(state["hist"]))
+            state["last_hist"] = list(state["hist"])
+            restart()
+        elif ph == "refine" and solver.mode == "switch" and norm <= solver.switch_threshold:
+            state["phase"] = "fp64"
+
+    restart()
+    for _ in range(max(3, a.warmup)):
+        step()
+    torch.cuda.synchronize()
+    ops.TIMER = ops.KernelTimer(min_points=n * n // 2)  # level-0 fused passes only
+    launches0 = _lib.call("mg_launch_count")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.call("mg_launch_count") - launches0
+    kern = ops.TIMER.summary()
+    ops.TIMER = None
+    value = n * n * a.steps / (ms * 1e-3)
+
+    # roofline of the dominant kernel (largest total time among the level-0 fused passes)
+    def alg_bytes(tag):
+        name, dt, _ = tag.split("/")
+        w = 8 if dt == "f64" else 4
+        if "resid32" in name or name.startswith("update"):
+            b = 0.0
+            if "resid32" in name:
+                b += 8 + 8 + 4            # read u64, f64; write r32
+            if name.startswith("update"):
+                b += 4 + 8                # read e32; write u64
+            return b * n * n
+        b = 3.0 * w                       # read u, read f, write u
+        if name.startswith("Z+"):
+            b -= w                        # the zero iterate is not read
+        if "P+" in name:
+            b += 0.25 * w                 # read the coarse correction
+        if "+R" in name:
+            b += 0.25 * w                 # write the restricted residual
+        return b * n * n
+    roof = None
+    kernels = {}
+    for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
+        ach = alg_bytes(tag) / (d["mean_ms"] * 1e-3) / 1e9
+        sweeps = int(tag.split("rbgs")[1][0]) if "rbgs" in tag else 0
+        w = 8 if "/f64/" in tag else 4
+        kernels[tag] = {"launches": d["launches"], "mean_ms": round(d["mean_ms"], 4), "hbm_gbs": round(ach, 1),
+                        "frac_of_peak": round(ach / peak, 4), "share_of_step": round(d["total_ms"] / ms, 4),
+                        "smoother_alg_gbs": round(3 * w * sweeps * n * n / (d["mean_ms"] * 1e-3) / 1e9, 1)}
+        if roof is None:
+            roof = {"bound": "hbm", "kernel": tag, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": alg_bytes(tag)}
+    tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if roof is not None and os.path.exists(tr):
+        try:
+            roof["traffic"] = json.load(open(tr)).get(roof["kernel"])
+        except Exception:
+            pass
+    cycle_frac = BYTES_PER_UNKNOWN_FP64_V22 * value / 1e9 / peak
+
+    # end to end through the public API with HOST buffers (pinned): H2D of f, solve, D2H of u
+    e2e = None
+    if not a.no_e2e:
+        f_host = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        f_host.copy_(b64.f)
+        torch.cuda.synchronize()
+        api = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
+                                      cycle_type=a.cycle, loader=a.loader, device=dev)
+        api._engine, api._shape, api._domain, api._grid, api._sumsq, api._pinned_out = (
+            solver._engine, solver._shape, solver._domain, solver._grid, solver._sumsq, None)
+        prob = PoissonProblem(rhs=f_host, nx=n, ny=n)
+        api.solve(prob)  # warm-up (allocates the pinned result staging)
+        reps, tot_t, tot_c, info = 3, 0.0, 0, None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            u_host, info = api.solve(prob)
+            tot_t += time.perf_counter() - t0
+            tot_c += info["iterations"]
+        e2e = {"value": n * n * tot_c / tot_t, "unit": UNIT, "h2d_bytes_per_step": n * n * 8,
+               "d2h_bytes_per_step": n * n * 8 + 8 * info["iterations"], "step": "one solve() call: pinned host f -> "
+               "device, %d cycles, device u -> pinned host" % info["iterations"], "seconds_per_solve": tot_t / reps,
+               "iterations": info["iterations"], "final_residual": info["final_residual"],
+               "max_error": float(ops.maxerr_sinsin(eng.levels[0].bufs(torch.float64).u))}
+        del f_host
+
+    cpu = None if a.no_cpu_baseline else run_cpu_baseline(a.cpu_n, 8)
+    clocks = clk.summary()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup),
+        "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 cycle / f64 iterate+residual" if solver.mode in ("switch", "refine") else
+                 ("f64" if solver.mode == "fp64" else "f32"),
+        "data": "synthetic",
+        "config": {"workload": f"2D Poisson {n}x{n} manufactured sin*sin, {a.cycle}(2,2) red-black GS, "
+                               f"precision_strategy={a.strategy} (BASELINE configs[2])", "levels": eng.num_levels,
+                   "loader": a.loader, "tolerance": tol, "switch_threshold": 1e-6, "l2": "inputs (>= 1 GB per array) exceed the 126 MB L2; no flush needed",
+                   "cycles_per_solve": state["cycles_per_solve"][-3:], "last_residual_history": state.get("last_hist")},
+        "roofline": roof, "kernels": kernels,
+        "cycle_roofline": {"bytes_per_unknown": BYTES_PER_UNKNOWN_FP64_V22, "note": "fp64 fused-minimum model, SURVEY 8d",
+                           "frac_of_peak": round(cycle_frac, 4)},
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)
+
+
+if __name__ == "__main__":
+    main()

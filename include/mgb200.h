@@ -54,6 +54,8 @@ MG_API int mg_abi_version(void);
 MG_API const char* mg_status_string(int status);
 /* number of SMs of the current device, cached per device (used by callers to size workspaces) */
 MG_API int mg_device_sm_count(void);
+/* process-wide count of CUDA kernels this library has launched (bench.py's gpu_launches) */
+MG_API long long mg_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Basic per-operator kernels (one reference method each)
@@ -170,6 +172,8 @@ MG_API int mg_maxerr_sinsin(const void* u, int nx, int ny, int64_t ld, double x0
 #define MG_VC_NORM 4             /* back stage: residual sum of squares into sumsq_out (needs workspace) */
 #define MG_VC_LOADER_CPASYNC 16  /* stage rows with per-lane cp.async instead of TMA */
 #define MG_VC_NO_STORE 32        /* do not write u_out (pure residual passes, sweeps = 0) */
+#define MG_VC_U_ZERO 64          /* u_in is identically zero and is not read (u_in may be NULL): the first
+                                    pre-smoothing pass of every coarse-level / error-equation solve */
 #define MG_VC_ROWS(r) (((r) & 0xFFF) << 8) /* override rows per tile (0 = auto) */
 
 /* doubles of workspace MG_VC_NORM needs for an (nx, ny) field */
@@ -179,6 +183,18 @@ MG_API int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* 
                double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
                int64_t ld_f, int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega,
                double coefficient, int sweeps, int dtype, int flags, void* stream);
+
+/* Mixed-precision defect-correction pass on the fp64 iterate ("fp32 smoothing / fp64 residual"; the
+ * reference's mixed_precision_residual_kernel + mixed_precision_correction_kernel,
+ * gpu/cuda_kernels.py:843-929, and the refinement loop of docs/methodology.md:337-360), one HBM pass:
+ *     u_out = u_in + (double) e_in            (e_in: fp32 fine-grid correction; NULL: u unchanged, no store)
+ *     r_out = (float) (f - coefficient*lap_h u_out)   (r_out: fp32; NULL: no residual stage)
+ *     sumsq_out[0] = sum over all points of the fp64 residual squared (needs workspace)
+ * u, f are fp64; out of place (u_out != u_in). */
+MG_API int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
+                      double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
+                      int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy, double coefficient,
+                      int flags, void* stream);
 
 /* `sweeps` temporally blocked RB-GS sweeps in one HBM pass (replaces GaussSeidelSmoother(red_black=True)
  * .smooth, smoothers.py:117-151; SmoothingKernels.red_black_gauss_seidel / block_gauss_seidel_kernel,

@@ -8,13 +8,16 @@
 // Thread mapping: threadIdx.x walks j (the contiguous index), rows are spread over
 // blockIdx.y/threadIdx.y, so every warp reads and writes contiguous row segments.
 #include <stdio.h>
+#include <atomic>
 #include "mg_common.cuh"
 
 namespace mg {
 
 static thread_local char g_err[256];
+static std::atomic<long long> g_launches{0};
 
-int check_launch(const char* what) {
+int check_launch(const char* what, int launches) {
+  g_launches.fetch_add(launches, std::memory_order_relaxed);
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -353,6 +356,8 @@ const char* mg_status_string(int status) {
 
 int mg_device_sm_count(void) { return mg::sm_count(); }
 
+long long mg_launch_count(void) { return mg::g_launches.load(std::memory_order_relaxed); }
+
 int mg_apply_laplacian(const void* u, void* out, int nx, int ny, int64_t ld_u, int64_t ld_out, double hx,
                        double hy, double coefficient, int dtype, void* stream) {
   MG_REQUIRE(u && out && nx >= 3 && ny >= 3 && ld_u >= ny && ld_out >= ny && hx > 0 && hy > 0);
@@ -407,7 +412,7 @@ int mg_smooth_rbgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t
         rbgs_colour_kernel<float><<<g, b, 0, st>>>((float*)u, (const float*)f, nx, ny, ld_u, ld_f, colour,
                                                    make_scalars<float>(hx, hy, omega, 1.0));
     }
-  return check_launch("mg_smooth_rbgs");
+  return check_launch("mg_smooth_rbgs", 2 * sweeps);
 }
 
 int mg_smooth_jacobi(void* u, void* tmp, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx,
@@ -432,7 +437,7 @@ int mg_smooth_jacobi(void* u, void* tmp, const void* f, int nx, int ny, int64_t 
     const size_t esz = dtype == MG_F64 ? 8 : 4;
     cudaMemcpy2DAsync(u, ld_u * esz, src, ld_u * esz, (size_t)ny * esz, nx, cudaMemcpyDeviceToDevice, st);
   }
-  return check_launch("mg_smooth_jacobi");
+  return check_launch("mg_smooth_jacobi", sweeps);
 }
 
 int mg_smooth_lexgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
@@ -537,7 +542,7 @@ int mg_sumsq(const void* x, int nx, int ny, int64_t ld, int dtype, double* works
   else
     sumsq_partial_kernel<float><<<blocks, RED_THREADS, 0, st>>>((const float*)x, nx, ny, ld, workspace);
   final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(workspace, blocks, out);
-  return check_launch("mg_sumsq");
+  return check_launch("mg_sumsq", 2);
 }
 
 int mg_cast(const void* src, void* dst, int nx, int ny, int64_t ld_src, int64_t ld_dst, int dtype_src,
@@ -579,7 +584,7 @@ int mg_zero(void* x, int nx, int64_t ld, int dtype, void* stream) {
   if (!valid_dtype(dtype)) return MG_ERR_DTYPE;
   const size_t esz = dtype == MG_F64 ? 8 : 4;
   cudaMemsetAsync(x, 0, (size_t)nx * ld * esz, as_stream(stream));
-  return check_launch("mg_zero");
+  return check_launch("mg_zero", 0);
 }
 
 int mg_fill_sinsin(void* f, int nx, int ny, int64_t ld, double x0, double x1, double y0, double y1,
@@ -609,7 +614,7 @@ int mg_maxerr_sinsin(const void* u, int nx, int ny, int64_t ld, double x0, doubl
     maxerr_partial_kernel<float><<<blocks, RED_THREADS, 0, st>>>((const float*)u, nx, ny, ld, x0, x1, y0, y1,
                                                                  amplitude, kx, ky, workspace);
   final_reduce_kernel<true><<<1, RED_THREADS, 0, st>>>(workspace, blocks, out);
-  return check_launch("mg_maxerr_sinsin");
+  return check_launch("mg_maxerr_sinsin", 2);
 }
 
 }  // extern "C"

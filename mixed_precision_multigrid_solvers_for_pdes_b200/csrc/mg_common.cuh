@@ -101,7 +101,7 @@ __device__ __forceinline__ double block_reduce(double v, double* red) {
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-int check_launch(const char* what);  // defined in mg_basic.cu
+int check_launch(const char* what, int launches = 1);  // defined in mg_basic.cu; also counts kernel launches
 int sm_count();
 // out[0] = sum of partials[0..n) in a fixed order (deterministic); defined in mg_basic.cu
 void reduce_partials_sum(const double* partials, int n, double* out, cudaStream_t st);

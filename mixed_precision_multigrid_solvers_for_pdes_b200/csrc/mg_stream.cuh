@@ -38,7 +38,8 @@ namespace stream {
 
 constexpr int LANE_V = 4;     // elements per lane per row
 constexpr int STRIP = 128;    // columns per warp strip
-constexpr int BACK_NONE = 0, BACK_RESTRICT = 1, BACK_NORM = 2;
+constexpr int BACK_NONE = 0, BACK_RESTRICT = 1, BACK_NORM = 2, BACK_RESID = 3;  // RESID: store fp32 residual + norm
+constexpr int FRONT_NONE = 0, FRONT_PROLONG = 1, FRONT_ADDFINE = 2;             // ADDFINE: u += (T)e, e fp32, fine grid
 constexpr int LOADER_TMA = 0, LOADER_CPASYNC = 1;
 
 template <int NU, int BACK> struct Geometry {
@@ -56,11 +57,14 @@ struct PassParams {
   const void* u_in;
   void* u_out;
   const void* f;
-  const void* coarse_in;   // e_c (FRONT) or null
+  const void* coarse_in;   // e_c (FRONT_PROLONG) or null
   void* coarse_out;        // restricted residual (BACK_RESTRICT) or null
-  double* partials;        // one double per warp (BACK_NORM) or null
+  const float* fine_in;    // fp32 fine-grid correction (FRONT_ADDFINE) or null
+  float* resid_out;        // fp32 fine-grid residual (BACK_RESID) or null
+  double* partials;        // one double per warp (BACK_NORM / BACK_RESID) or null
   int nx, ny, nxc, nyc;
-  int64_t ld_in, ld_out, ld_f, ld_ci, ld_co;
+  int64_t ld_in, ld_out, ld_f, ld_ci, ld_co, ld_fi, ld_ro;
+  int u_zero;              // 1: u_in is identically zero and is not read
   int rows_per_tile;       // R (even)
   int nstrips;
   int store_u;             // 0: do not write u_out (pure residual passes)
@@ -108,6 +112,8 @@ template <typename T> __device__ __forceinline__ T shfl_dn1(T v) { return __shfl
 
 // 4 contiguous elements  <->  shared / global memory
 template <typename T> struct Row4 { T v[4]; };
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
 
 __device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
   const float4 t = *reinterpret_cast<const float4*>(p);
@@ -152,23 +158,28 @@ __device__ __forceinline__ T residual_fast(const StencilScalars<T>& s, T uc, T u
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NU, bool PROLONG, int BACK, int LOADER, int WARPS, int NSTAGE, int RB>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, int WARPS, int NSTAGE, int RB>
 __global__ void __launch_bounds__(WARPS * 32)
     rbgs_stream_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_f,
-                       const PassParams p, const StencilScalars<T> sc) {
+                       const __grid_constant__ CUtensorMap map_e, const PassParams p, const StencilScalars<T> sc) {
   using G = Geometry<NU, BACK>;
   static_assert(RB % 2 == 0, "row parity must be static inside a box");
+  static_assert(FRONT != FRONT_ADDFINE || sizeof(T) == 8, "ADDFINE adds an fp32 correction to an fp64 iterate");
+  static_assert(BACK != BACK_RESID || sizeof(T) == 8, "RESID rounds an fp64 residual to fp32");
   constexpr int WR = G::WR, FR = G::FR;
+  constexpr bool HAS_BACK = BACK != BACK_NONE;
+  constexpr bool HAS_NORM = BACK == BACK_NORM || BACK == BACK_RESID;
   constexpr uint32_t ROW_BYTES = STRIP * sizeof(T);
-  constexpr uint32_t BOX_BYTES = RB * ROW_BYTES;  // one array, one stage
+  constexpr uint32_t BOX_BYTES = RB * ROW_BYTES;                            // one T array, one stage
+  constexpr uint32_t EBOX_BYTES = FRONT == FRONT_ADDFINE ? RB * STRIP * 4 : 0;  // fp32 correction box
+  constexpr uint32_t STAGE_BYTES = 2 * BOX_BYTES + EBOX_BYTES;
 
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[WARPS][NSTAGE];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x * WARPS + warp;
-  // ring of this warp: [stage][array(u,f)][RB][STRIP]
-  unsigned char* ring = smem + (size_t)warp * NSTAGE * 2 * BOX_BYTES;
+  unsigned char* ring = smem + (size_t)warp * NSTAGE * STAGE_BYTES;  // [stage][u box | f box | e box]
 
   if (LOADER == LOADER_TMA) {
     if (lane == 0) {
@@ -180,7 +191,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     __syncwarp();
   }
   if (strip >= p.nstrips) {  // warp-uniform; warps never synchronise with each other
-    if (BACK == BACK_NORM && lane == 0) p.partials[(size_t)blockIdx.y * (gridDim.x * WARPS) + strip] = 0.0;
+    if (HAS_NORM && lane == 0) p.partials[(size_t)blockIdx.y * (gridDim.x * WARPS) + strip] = 0.0;
     return;
   }
 
@@ -188,10 +199,13 @@ __global__ void __launch_bounds__(WARPS * 32)
   const int g0 = strip * G::STRIDE - 4;  // global column of local column 0 (multiple of 4)
   const int jbase = g0 + lane * LANE_V;  // global column of this lane's element 0
   const int I0 = blockIdx.y * p.rows_per_tile;
-  const int I1 = min(I0 + p.rows_per_tile, nx);                                    // owned rows [I0, I1)
-  const int i_begin = I0 - G::ROW_LEAD;                                            // even
-  const int i_last = min(I0 + p.rows_per_tile, nx) - 1 + G::ROW_TAIL;
+  const int I1 = min(I0 + p.rows_per_tile, nx);  // owned rows [I0, I1)
+  const int i_begin = I0 - G::ROW_LEAD;          // even
+  const int i_last = I1 - 1 + G::ROW_TAIL;
   const int nbox = (i_last - i_begin + 1 + RB - 1) / RB;
+  const bool u_zero = p.u_zero != 0;
+  // a strip whose 128 columns are all interior needs no column masks
+  const bool strip_interior = (g0 >= 1) && (g0 + STRIP - 1 <= ny - 2);
 
   // per-element masks
   uint32_t upd = 0, dom = 0, own = 0;
@@ -208,20 +222,22 @@ __global__ void __launch_bounds__(WARPS * 32)
   // ---- loader ----------------------------------------------------------------------------------
   auto issue_box = [&](int box) {
     const int stage = box % NSTAGE;
-    unsigned char* dst_u = ring + (size_t)stage * 2 * BOX_BYTES;
+    unsigned char* dst_u = ring + (size_t)stage * STAGE_BYTES;
     unsigned char* dst_f = dst_u + BOX_BYTES;
+    unsigned char* dst_e = dst_f + BOX_BYTES;
     const int row0 = i_begin + box * RB;
     if (LOADER == LOADER_TMA) {
       if (lane == 0) {
-        mbar_expect_tx(&full_bar[warp][stage], 2 * BOX_BYTES);
-        tma_load_2d(dst_u, &map_u, g0, row0, &full_bar[warp][stage]);
+        mbar_expect_tx(&full_bar[warp][stage], (u_zero ? 0u : BOX_BYTES) + BOX_BYTES + EBOX_BYTES);
+        if (!u_zero) tma_load_2d(dst_u, &map_u, g0, row0, &full_bar[warp][stage]);
         tma_load_2d(dst_f, &map_f, g0, row0, &full_bar[warp][stage]);
+        if (FRONT == FRONT_ADDFINE) tma_load_2d(dst_e, &map_e, g0, row0, &full_bar[warp][stage]);
       }
     } else {
       // per lane: its own 4 elements of every row of the box; zero-fill outside the domain
       int nvalid = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) nvalid += (jbase + e >= 0 && jbase + e < ny) ? 1 : 0;  // valid run starts at e=0 or is empty
+      for (int e = 0; e < 4; ++e) nvalid += (jbase + e >= 0 && jbase + e < ny) ? 1 : 0;  // a prefix, or empty
       const bool colok = (jbase >= 0) && nvalid > 0;
       const int jc = colok ? jbase : 0;
 #pragma unroll
@@ -235,14 +251,19 @@ __global__ void __launch_bounds__(WARPS * 32)
         unsigned char* du = dst_u + r * ROW_BYTES + lane * LANE_V * sizeof(T);
         unsigned char* df = dst_f + r * ROW_BYTES + lane * LANE_V * sizeof(T);
         if (sizeof(T) == 4) {
-          cp_async16(du, su, bytes);
+          if (!u_zero) cp_async16(du, su, bytes);
           cp_async16(df, sf, bytes);
         } else {
-          cp_async16(du, su, min(bytes, 16));
-          cp_async16(du + 16, su + 2, max(bytes - 16, 0));
+          if (!u_zero) {
+            cp_async16(du, su, min(bytes, 16));
+            cp_async16(du + 16, su + 2, max(bytes - 16, 0));
+          }
           cp_async16(df, sf, min(bytes, 16));
           cp_async16(df + 16, sf + 2, max(bytes - 16, 0));
         }
+        if (FRONT == FRONT_ADDFINE)
+          cp_async16(dst_e + r * STRIP * 4 + lane * LANE_V * 4, p.fine_in + (int64_t)rc * p.ld_fi + jc,
+                     ok ? nvalid * 4 : 0);
       }
     }
   };
@@ -270,15 +291,18 @@ __global__ void __launch_bounds__(WARPS * 32)
   for (int a = 0; a < 3; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) rr[a][e] = (T)0;
-  double acc = 0.0;  // BACK_NORM
+  double acc = 0.0;  // sum of squared residuals
 
-  // coarse correction rows (FRONT): c0 = coarse row floor(i/2), c1 = the next one; 3 columns each
+  // coarse correction rows (FRONT_PROLONG): c0 = coarse row floor(i/2), c1 = the next one; 3 columns each
   T c0[3] = {(T)0, (T)0, (T)0}, c1[3] = {(T)0, (T)0, (T)0};
   const int jc0 = (g0 >> 1) + 2 * lane;  // coarse column of element 0 (g0 is a multiple of 4, may be -4)
-  auto load_coarse_row = [&](int ic, T(&c)[3]) {
+  auto load_coarse_row = [&](int ic, T(&c)[3], bool checked) {
     T a = (T)0, b = (T)0, d = (T)0;
-    if (ic >= 0 && ic < p.nxc) {
-      const T* row = reinterpret_cast<const T*>(p.coarse_in) + (int64_t)ic * p.ld_ci;
+    const T* row = reinterpret_cast<const T*>(p.coarse_in) + (int64_t)ic * p.ld_ci;
+    if (!checked) {
+      ldg2(row + jc0, a, b);
+      if (lane == 31) d = __ldg(row + jc0 + 2);
+    } else if (ic >= 0 && ic < p.nxc) {
       if (jc0 >= 0 && jc0 + 1 < p.nyc) {
         ldg2(row + jc0, a, b);
       } else {
@@ -290,32 +314,25 @@ __global__ void __launch_bounds__(WARPS * 32)
     const T nxt = shfl_dn1(a);
     c[0] = a; c[1] = b; c[2] = (lane == 31) ? d : nxt;
   };
-  if (PROLONG) {
-    load_coarse_row(i_begin >> 1, c0);  // i_begin is even; >> floors for negatives
-    load_coarse_row((i_begin >> 1) + 1, c1);
+  if (FRONT == FRONT_PROLONG) {
+    load_coarse_row(i_begin >> 1, c0, true);  // i_begin is even; >> floors for negatives
+    load_coarse_row((i_begin >> 1) + 1, c1, true);
   }
 
   T* const uout = reinterpret_cast<T*>(p.u_out);
   T* const cout = reinterpret_cast<T*>(p.coarse_out);
+  const bool store_u = p.store_u != 0;
 
-  // ---- main loop over boxes ----------------------------------------------------------------------
-  for (int box = 0; box < nbox; ++box) {
-    const int stage = box % NSTAGE;
-    if (LOADER == LOADER_TMA) {
-      mbar_wait(&full_bar[warp][stage], (uint32_t)((box / NSTAGE) & 1));
-    } else {
-      cp_async_wait<NSTAGE - 1>();
-      __syncwarp();
-    }
-    const T* su = reinterpret_cast<const T*>(ring + (size_t)stage * 2 * BOX_BYTES) + lane * LANE_V;
-    const T* sf = su + RB * STRIP;
-
+  // ---- one box of RB rows.  MASKED = false is the interior fast path: every row and column the box
+  //      touches is an interior point, so there are no boundary tests, selects or divergent branches. ----
+  auto process_box = [&](auto masked_tag, const int ib, const T* su, const T* sf, const float* se) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
 #pragma unroll
     for (int k = 0; k < RB; ++k) {
-      const int i = i_begin + box * RB + k;  // newest row; parity of i == parity of k
+      const int i = ib + k;  // newest row; parity of i == parity of k
       const int kpar = k & 1;
 
-      // (0) shift the windows by one row
+      // (0) shift the windows by one row (register renaming after unrolling)
 #pragma unroll
       for (int a = WR - 1; a > 0; --a)
 #pragma unroll
@@ -326,32 +343,43 @@ __global__ void __launch_bounds__(WARPS * 32)
         for (int e = 0; e < 4; ++e) fr[a][e] = fr[a - 1][e];
 
       // (1) newest row from the ring
-      lds4(su + k * STRIP, w[0]);
+      if (u_zero) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[0][e] = (T)0;
+      } else {
+        lds4(su + k * STRIP, w[0]);
+      }
       lds4(sf + k * STRIP, fr[0]);
 
-      // (1b) FRONT: u += bilinear prolongation of the coarse correction (transfer.py:234-267 semantics)
-      if (PROLONG) {
-        if (i >= 0 && i < nx) {
+      // (1a) FRONT_ADDFINE: u += (T)e  (rows/columns outside the domain hold zeros in both arrays)
+      if (FRONT == FRONT_ADDFINE) {
+        const float4 ev = *reinterpret_cast<const float4*>(se + k * STRIP);
+        w[0][0] += (T)ev.x; w[0][1] += (T)ev.y; w[0][2] += (T)ev.z; w[0][3] += (T)ev.w;
+      }
+
+      // (1b) FRONT_PROLONG: u += bilinear prolongation of the coarse correction (transfer.py:234-267 semantics)
+      if (FRONT == FRONT_PROLONG) {
+        if (!MASKED || (i >= 0 && i < nx)) {
           T add[4];
           if (kpar == 0) {  // even fine row: coarse row i/2
-            const bool last = (i == nx - 1);
+            const bool last = MASKED && (i == nx - 1);
             add[0] = c0[0];
             add[2] = c0[1];
             add[1] = last ? (T)0 : (T)0.5 * (c0[0] + c0[1]);
             add[3] = last ? (T)0 : (T)0.5 * (c0[1] + c0[2]);
           } else {  // odd fine row: coarse rows (i-1)/2 and (i+1)/2
-            add[0] = (jbase == ny - 1) ? (T)0 : (T)0.5 * (c0[0] + c1[0]);
-            add[2] = (jbase + 2 == ny - 1) ? (T)0 : (T)0.5 * (c0[1] + c1[1]);
+            add[0] = (MASKED && jbase == ny - 1) ? (T)0 : (T)0.5 * (c0[0] + c1[0]);
+            add[2] = (MASKED && jbase + 2 == ny - 1) ? (T)0 : (T)0.5 * (c0[1] + c1[1]);
             add[1] = (T)0.25 * (((c0[0] + c0[1]) + c1[0]) + c1[1]);
             add[3] = (T)0.25 * (((c0[1] + c0[2]) + c1[1]) + c1[2]);
           }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) w[0][e] = ((dom >> e) & 1u) ? w[0][e] + add[e] : w[0][e];
+          for (int e = 0; e < 4; ++e) w[0][e] = (!MASKED || ((dom >> e) & 1u)) ? w[0][e] + add[e] : w[0][e];
         }
         if (kpar == 1) {  // moving to the next coarse row pair
 #pragma unroll
           for (int e = 0; e < 3; ++e) c0[e] = c1[e];
-          load_coarse_row(((i + 1) >> 1) + 1, c1);
+          load_coarse_row(((i + 1) >> 1) + 1, c1, MASKED);
         }
       }
 
@@ -359,21 +387,21 @@ __global__ void __launch_bounds__(WARPS * 32)
 #pragma unroll
       for (int s = 1; s <= 2 * NU; ++s) {
         const int q = i - s;
-        if (q >= 1 && q <= nx - 2) {  // warp-uniform
+        if (!MASKED || (q >= 1 && q <= nx - 2)) {  // warp-uniform
           // colour of stage s is (s-1)&1 (red = (row+col) even first); col parity == element parity
-          const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element (0 or 1), compile-time after unrolling
+          const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element, compile-time after unrolling
           if (e0 == 0) {
             const T lfx = shfl_up1(w[s][3]);
             const T n0 = relax_fast<T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
             const T n2 = relax_fast<T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
-            w[s][0] = (upd & 1u) ? n0 : w[s][0];
-            w[s][2] = (upd & 4u) ? n2 : w[s][2];
+            w[s][0] = (!MASKED || (upd & 1u)) ? n0 : w[s][0];
+            w[s][2] = (!MASKED || (upd & 4u)) ? n2 : w[s][2];
           } else {
             const T rtx = shfl_dn1(w[s][0]);
             const T n1 = relax_fast<T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
             const T n3 = relax_fast<T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
-            w[s][1] = (upd & 2u) ? n1 : w[s][1];
-            w[s][3] = (upd & 8u) ? n3 : w[s][3];
+            w[s][1] = (!MASKED || (upd & 2u)) ? n1 : w[s][1];
+            w[s][3] = (!MASKED || (upd & 8u)) ? n3 : w[s][3];
           }
         }
       }
@@ -381,10 +409,13 @@ __global__ void __launch_bounds__(WARPS * 32)
       // (3) the row of age 2NU is final: store the owned part
       {
         const int qf = i - 2 * NU;
-        if (p.store_u && qf >= I0 && qf < I1 && qf < nx && own != 0u) {
+        if (store_u && qf >= I0 && qf < I1 && own != 0u) {
           T* dst = uout + (int64_t)qf * p.ld_out + jbase;
           if (own == 0xFu) {
             stg4(dst, w[2 * NU]);
+          } else if (!MASKED) {  // interior strip: ownership changes only at even columns
+            if ((own & 3u) == 3u) stg2(dst, w[2 * NU][0], w[2 * NU][1]);
+            if ((own & 12u) == 12u) stg2(dst + 2, w[2 * NU][2], w[2 * NU][3]);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -394,33 +425,43 @@ __global__ void __launch_bounds__(WARPS * 32)
       }
 
       // (4) BACK: residual of the row of age 2NU+1 (its neighbours are final)
-      if (BACK != BACK_NONE) {
+      if (HAS_BACK) {
         constexpr int A = 2 * NU + 1;
         const int q2 = i - A;
         T r[4] = {(T)0, (T)0, (T)0, (T)0};
-        if (q2 >= 0 && q2 < nx) {
-          if (q2 >= 1 && q2 <= nx - 2) {
+        if (!MASKED || (q2 >= 0 && q2 < nx)) {
+          if (!MASKED || (q2 >= 1 && q2 <= nx - 2)) {
             const T lfx = shfl_up1(w[A][3]);
             const T rtx = shfl_dn1(w[A][0]);
             const T r0 = residual_fast<T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
             const T r1 = residual_fast<T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
             const T r2 = residual_fast<T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
             const T r3 = residual_fast<T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
-            r[0] = (upd & 1u) ? r0 : fr[A][0];
-            r[1] = (upd & 2u) ? r1 : fr[A][1];
-            r[2] = (upd & 4u) ? r2 : fr[A][2];
-            r[3] = (upd & 8u) ? r3 : fr[A][3];
+            r[0] = (!MASKED || (upd & 1u)) ? r0 : fr[A][0];
+            r[1] = (!MASKED || (upd & 2u)) ? r1 : fr[A][1];
+            r[2] = (!MASKED || (upd & 4u)) ? r2 : fr[A][2];
+            r[3] = (!MASKED || (upd & 8u)) ? r3 : fr[A][3];
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e) r[e] = fr[A][e];  // boundary rows: r = f (laplacian.py:64,117)
           }
         }
-        if (BACK == BACK_NORM) {
-          if (q2 >= I0 && q2 < I1 && q2 < nx) {
+        if (HAS_NORM) {
+          if (q2 >= I0 && q2 < I1) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const T sq = r[e] * r[e];  // squared in T like NumPy's field**2, accumulated in fp64
               acc += ((own >> e) & 1u) ? (double)sq : 0.0;
+            }
+            if (BACK == BACK_RESID && own != 0u) {
+              float* dst = p.resid_out + (int64_t)q2 * p.ld_ro + jbase;
+              if (own == 0xFu) {
+                *reinterpret_cast<float4*>(dst) = make_float4((float)r[0], (float)r[1], (float)r[2], (float)r[3]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if ((own >> e) & 1u) dst[e] = (float)r[e];
+              }
             }
           }
         } else {  // BACK_RESTRICT
@@ -433,23 +474,23 @@ __global__ void __launch_bounds__(WARPS * 32)
           if (kpar == 0) {  // q2 = i - 2NU - 1 is odd: rows q2-2, q2-1 (centre, even), q2 are complete
             const int fi = q2 - 1;  // fine centre row
             const int ic = fi >> 1;
-            if (fi >= I0 && fi < I1 && fi >= 0 && ic < p.nxc) {  // owned coarse row (warp-uniform)
+            if (fi >= I0 && fi < I1) {  // owned coarse row (warp-uniform); I0 >= 0, I1 <= nx
               const T l2 = shfl_up1(rr[2][3]), l1 = shfl_up1(rr[1][3]), l0 = shfl_up1(rr[0][3]);
-              const bool brow = (ic == 0 || ic == p.nxc - 1);
+              const bool brow = MASKED && (ic == 0 || ic == p.nxc - 1);
               // element 0 -> coarse column jc0, element 2 -> coarse column jc0 + 1
               T v0, v1;
               {
                 const T corners = ((l2 + rr[2][1]) + l0) + rr[0][1];
                 const T edges = ((rr[2][0] + rr[0][0]) + l1) + rr[1][1];
                 v0 = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * rr[1][0];
-                const bool b = brow || jc0 == 0 || jc0 == p.nyc - 1;
+                const bool b = MASKED && (brow || jc0 == 0 || jc0 == p.nyc - 1);
                 v0 = b ? rr[1][0] : v0;
               }
               {
                 const T corners = ((rr[2][1] + rr[2][3]) + rr[0][1]) + rr[0][3];
                 const T edges = ((rr[2][2] + rr[0][2]) + rr[1][1]) + rr[1][3];
                 v1 = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * rr[1][2];
-                const bool b = brow || jc0 + 1 == 0 || jc0 + 1 == p.nyc - 1;
+                const bool b = MASKED && (brow || jc0 + 1 == 0 || jc0 + 1 == p.nyc - 1);
                 v1 = b ? rr[1][2] : v1;
               }
               const bool o0 = (own & 1u) != 0u, o1 = (own & 4u) != 0u;
@@ -465,6 +506,28 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
       }
     }  // rows of the box
+  };
+
+  // ---- main loop over boxes ----------------------------------------------------------------------
+  for (int box = 0; box < nbox; ++box) {
+    const int stage = box % NSTAGE;
+    if (LOADER == LOADER_TMA) {
+      mbar_wait(&full_bar[warp][stage], (uint32_t)((box / NSTAGE) & 1));
+    } else {
+      cp_async_wait<NSTAGE - 1>();
+      __syncwarp();
+    }
+    const T* su = reinterpret_cast<const T*>(ring + (size_t)stage * STAGE_BYTES) + lane * LANE_V;
+    const T* sf = su + RB * STRIP;
+    const float* se = reinterpret_cast<const float*>(ring + (size_t)stage * STAGE_BYTES + 2 * BOX_BYTES) + lane * LANE_V;
+    const int ib = i_begin + box * RB;
+    // interior fast path: every row evaluated in this box (oldest: ib - 2NU - 1 with a BACK stage) and the
+    // newest row ib + RB - 1 are interior rows, and the strip has no boundary column
+    // (with restriction also the centre row q2 - 1 of the oldest coarse row, hence 3 instead of 1)
+    constexpr int OLDEST = 2 * NU + (BACK == BACK_RESTRICT ? 3 : (HAS_BACK ? 1 : 0));
+    const bool fast = strip_interior && (ib - OLDEST >= 1) && (ib + RB - 1 <= nx - 2);
+    if (fast) process_box(FalseTag{}, ib, su, sf, se);
+    else process_box(TrueTag{}, ib, su, sf, se);
 
     // refill this stage with box + NSTAGE
     __syncwarp();
@@ -472,7 +535,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     if (LOADER == LOADER_CPASYNC) cp_async_commit();
   }
 
-  if (BACK == BACK_NORM) {
+  if (HAS_NORM) {
     acc = warp_sum(acc);
     if (lane == 0) p.partials[(size_t)blockIdx.y * (gridDim.x * WARPS) + strip] = acc;
   }

@@ -1,20 +1,14 @@
 // libmgb200: C ABI of the fused / temporally blocked V-cycle passes (mg_vc_* family).
 #include <cudaTypedefs.h>
-#include "mg_stream.cuh"
+#include <string.h>
+#include "mg_stream_inst.cuh"
 
 namespace mg {
 namespace stream {
-int launch_pass_f32_tma(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
-                        const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f32_cpa(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
-                        const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f64_tma(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
-                        const StencilScalars<double>&, cudaStream_t);
-int launch_pass_f64_cpa(int, bool, int, const CUtensorMap&, const CUtensorMap&, const PassParams&,
-                        const StencilScalars<double>&, cudaStream_t);
-
-constexpr int WARPS = 4;
-constexpr int RB = 4;
+int launch_pass_f32_tma(int, int, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f32_cpa(int, int, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_tma(int, int, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f64_cpa(int, int, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -70,6 +64,84 @@ static inline int pick_rows(int nx, int nstrips, int override_rows) {
 using namespace mg;
 using namespace mg::stream;
 
+// Shared argument checking + launch for every mg_vc_* entry point.
+static int run_pass(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
+                    const float* fine_in, float* resid_out, double* sumsq_out, double* workspace, int nx, int ny,
+                    int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_ci, int64_t ld_co, int64_t ld_fi,
+                    int64_t ld_ro, double hx, double hy, double omega, double coefficient, int sweeps, int dtype,
+                    int front, int back, int flags, void* stream, const char* what) {
+  const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
+  const bool store = (flags & MG_VC_NO_STORE) == 0;
+  const bool u_zero = (flags & MG_VC_U_ZERO) != 0;
+  const int rows_override = (flags >> 8) & 0xFFF;
+  if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
+  if (!f || nx < 3 || ny < 3 || ld_f < ny || hx <= 0 || hy <= 0) return MG_ERR_BADARG;
+  if (!u_zero && (!u_in || ld_in < ny)) return MG_ERR_BADARG;
+  if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
+  if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
+  if (!store && back == BACK_NONE) return MG_ERR_BADARG;
+  if (sweeps == 0 && front == FRONT_NONE && back == BACK_NONE) return MG_ERR_BADARG;
+  const int nxc = (nx - 1) / 2 + 1, nyc = (ny - 1) / 2 + 1;
+  if (front == FRONT_PROLONG || back == BACK_RESTRICT) {
+    if ((nx - 1) % 2 || (ny - 1) % 2) return MG_ERR_BADARG;
+    if (front == FRONT_PROLONG && (!coarse_in || ld_ci < nyc)) return MG_ERR_BADARG;
+    if (back == BACK_RESTRICT && (!coarse_out || ld_co < nyc)) return MG_ERR_BADARG;
+  }
+  if (front == FRONT_ADDFINE && (!fine_in || ld_fi < ny || dtype != MG_F64)) return MG_ERR_BADARG;
+  if (back == BACK_RESID && (!resid_out || ld_ro < ny || dtype != MG_F64)) return MG_ERR_BADARG;
+  const bool norm = back == BACK_NORM || back == BACK_RESID;
+  if (norm && (!sumsq_out || !workspace)) return MG_ERR_BADARG;
+  const size_t esz = dtype == MG_F64 ? 8 : 4;
+  auto misaligned = [&](const void* p, int64_t ld, size_t es) {
+    return p && (((uintptr_t)p & 15u) || (ld % (int64_t)(16 / es)));
+  };
+  if ((!u_zero && misaligned(u_in, ld_in, esz)) || misaligned(f, ld_f, esz) || (store && misaligned(u_out, ld_out, esz)) ||
+      (front == FRONT_PROLONG && misaligned(coarse_in, ld_ci, esz)) ||
+      (back == BACK_RESTRICT && misaligned(coarse_out, ld_co, esz)) ||
+      (front == FRONT_ADDFINE && misaligned(fine_in, ld_fi, 4)) || (back == BACK_RESID && misaligned(resid_out, ld_ro, 4)))
+    return MG_ERR_ALIGN;
+
+  PassParams p;
+  memset(&p, 0, sizeof(p));
+  p.u_in = u_zero ? f : u_in;  // never dereferenced when u_zero
+  p.u_out = u_out; p.f = f; p.coarse_in = coarse_in; p.coarse_out = coarse_out;
+  p.fine_in = fine_in; p.resid_out = resid_out;
+  p.partials = workspace;
+  p.nx = nx; p.ny = ny; p.nxc = nxc; p.nyc = nyc;
+  p.ld_in = u_zero ? ld_f : ld_in; p.ld_out = ld_out; p.ld_f = ld_f; p.ld_ci = ld_ci; p.ld_co = ld_co;
+  p.ld_fi = ld_fi; p.ld_ro = ld_ro;
+  p.u_zero = u_zero ? 1 : 0;
+  p.nstrips = num_strips(ny, sweeps, back);
+  p.rows_per_tile = pick_rows(nx, p.nstrips, rows_override);
+  p.store_u = store ? 1 : 0;
+
+  Maps m;
+  memset(&m, 0, sizeof(m));
+  if (!cpa) {
+    int rc = MG_OK;
+    if (!u_zero) rc = make_map(&m.u, u_in, nx, ny, ld_in, dtype);
+    if (rc == MG_OK) rc = make_map(&m.f, f, nx, ny, ld_f, dtype);
+    if (rc == MG_OK && front == FRONT_ADDFINE) rc = make_map(&m.e, fine_in, nx, ny, ld_fi, MG_F32);
+    if (rc != MG_OK) return rc;
+  }
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if (dtype == MG_F64) {
+    auto sc = make_scalars<double>(hx, hy, omega, coefficient);
+    rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, m, p, sc, st) : launch_pass_f64_tma(sweeps, front, back, m, p, sc, st);
+  } else {
+    auto sc = make_scalars<float>(hx, hy, omega, coefficient);
+    rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, m, p, sc, st) : launch_pass_f32_tma(sweeps, front, back, m, p, sc, st);
+  }
+  if (rc != MG_OK) return rc;
+  if (norm) {
+    const int ntiles = (nx + p.rows_per_tile - 1) / p.rows_per_tile;
+    const int n = ((p.nstrips + WARPS - 1) / WARPS) * WARPS * ntiles;
+    reduce_partials_sum(workspace, n, sumsq_out, st);
+  }
+  return check_launch(what, norm ? 2 : 1);
+}
+
 extern "C" {
 
 int mg_vc_workspace_doubles(int nx, int ny) {
@@ -83,68 +155,24 @@ int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* coarse_
                double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
                int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega, double coefficient, int sweeps,
                int dtype, int flags, void* stream) {
-  const bool prolong = (flags & MG_VC_PROLONG) != 0;
-  const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
-  const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
-  const bool store = (flags & MG_VC_NO_STORE) == 0;
-  const int rows_override = (flags >> 8) & 0xFFF;
-  if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
-  if (!u_in || !f || nx < 3 || ny < 3 || ld_in < ny || ld_f < ny || hx <= 0 || hy <= 0) return MG_ERR_BADARG;
-  if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
   if ((flags & MG_VC_RESTRICT) && (flags & MG_VC_NORM)) return MG_ERR_UNSUPPORTED;
-  if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
-  if (!store && back == BACK_NONE) return MG_ERR_BADARG;
-  if (sweeps == 0 && !prolong && back == BACK_NONE) return MG_ERR_BADARG;
-  const int nxc = (nx - 1) / 2 + 1, nyc = (ny - 1) / 2 + 1;
-  if (prolong || back == BACK_RESTRICT) {
-    if ((nx - 1) % 2 || (ny - 1) % 2) return MG_ERR_BADARG;
-    if (prolong && (!coarse_in || ld_ci < nyc)) return MG_ERR_BADARG;
-    if (back == BACK_RESTRICT && (!coarse_out || ld_co < nyc)) return MG_ERR_BADARG;
-  }
-  if (back == BACK_NORM && (!sumsq_out || !workspace)) return MG_ERR_BADARG;
-  const size_t esz = dtype == MG_F64 ? 8 : 4;
-  const int64_t va = 16 / (int64_t)esz;
-  auto misaligned = [&](const void* p, int64_t ld) { return p && (((uintptr_t)p & 15u) || (ld % va)); };
-  if (misaligned(u_in, ld_in) || misaligned(f, ld_f) || (store && misaligned(u_out, ld_out)) ||
-      (prolong && misaligned(coarse_in, ld_ci)) || (back == BACK_RESTRICT && misaligned(coarse_out, ld_co)))
-    return MG_ERR_ALIGN;
+  const int front = (flags & MG_VC_PROLONG) ? FRONT_PROLONG : FRONT_NONE;
+  const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
+  return run_pass(u_in, u_out, f, coarse_in, coarse_out, nullptr, nullptr, sumsq_out, workspace, nx, ny, ld_in, ld_out,
+                  ld_f, ld_ci, ld_co, 0, 0, hx, hy, omega, coefficient, sweeps, dtype, front, back, flags, stream,
+                  "mg_vc_pass");
+}
 
-  PassParams p;
-  p.u_in = u_in; p.u_out = u_out; p.f = f; p.coarse_in = coarse_in; p.coarse_out = coarse_out;
-  p.partials = workspace;
-  p.nx = nx; p.ny = ny; p.nxc = nxc; p.nyc = nyc;
-  p.ld_in = ld_in; p.ld_out = ld_out; p.ld_f = ld_f; p.ld_ci = ld_ci; p.ld_co = ld_co;
-  p.nstrips = num_strips(ny, sweeps, back);
-  p.rows_per_tile = pick_rows(nx, p.nstrips, rows_override);
-  p.store_u = store ? 1 : 0;
-
-  CUtensorMap mu, mf;
-  memset(&mu, 0, sizeof(mu));
-  memset(&mf, 0, sizeof(mf));
-  if (!cpa) {
-    int rc = make_map(&mu, u_in, nx, ny, ld_in, dtype);
-    if (rc != MG_OK) return rc;
-    rc = make_map(&mf, f, nx, ny, ld_f, dtype);
-    if (rc != MG_OK) return rc;
-  }
-  cudaStream_t st = as_stream(stream);
-  int rc;
-  if (dtype == MG_F64) {
-    auto sc = make_scalars<double>(hx, hy, omega, coefficient);
-    rc = cpa ? launch_pass_f64_cpa(sweeps, prolong, back, mu, mf, p, sc, st)
-             : launch_pass_f64_tma(sweeps, prolong, back, mu, mf, p, sc, st);
-  } else {
-    auto sc = make_scalars<float>(hx, hy, omega, coefficient);
-    rc = cpa ? launch_pass_f32_cpa(sweeps, prolong, back, mu, mf, p, sc, st)
-             : launch_pass_f32_tma(sweeps, prolong, back, mu, mf, p, sc, st);
-  }
-  if (rc != MG_OK) return rc;
-  if (back == BACK_NORM) {
-    const int ntiles = (nx + p.rows_per_tile - 1) / p.rows_per_tile;
-    const int n = ((p.nstrips + WARPS - 1) / WARPS) * WARPS * ntiles;
-    reduce_partials_sum(workspace, n, sumsq_out, st);
-  }
-  return check_launch("mg_vc_pass");
+int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out, double* sumsq_out,
+                      double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_e,
+                      int64_t ld_r, double hx, double hy, double coefficient, int flags, void* stream) {
+  const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
+  const int back = r_out ? BACK_RESID : BACK_NONE;
+  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_U_ZERO);
+  if (!e_in) fl |= MG_VC_NO_STORE;  // nothing to add: u is unchanged, only the residual is produced
+  return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
+                  workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,
+                  back, fl, stream, "mg_vc_defect_pass");
 }
 
 int mg_vc_smooth(const void* u_in, void* u_out, const void* f, int nx, int ny, int64_t ld_in, int64_t ld_out,

@@ -1,5 +1,5 @@
 // Host-side launcher for rbgs_stream_kernel, instantiated per (T, LOADER) translation unit to
-// keep compile times parallel.  Included by mg_stream_f32_tma.cu etc. with MG_T / MG_LOADER set.
+// keep compile times parallel.  Included by mg_stream_f32_tma.cu etc.
 #pragma once
 #include "mg_stream.cuh"
 
@@ -9,15 +9,20 @@ namespace stream {
 constexpr int WARPS = 4;
 constexpr int RB = 4;
 
-template <typename T> struct Stages { static constexpr int N = 4; };
-template <> struct Stages<double> { static constexpr int N = 3; };
+// ring depth: 3 boxes of 4 rows in flight per warp (fp32: 12 KB/warp), 2 for fp64 (16 KB/warp)
+template <typename T> struct Stages { static constexpr int N = 3; };
+template <> struct Stages<double> { static constexpr int N = 2; };
 
-template <typename T, int NU, bool PROLONG, int BACK, int LOADER>
-static int launch_one(const CUtensorMap& mu, const CUtensorMap& mf, const PassParams& p, const StencilScalars<T>& sc,
-                      cudaStream_t st) {
+struct Maps {
+  CUtensorMap u, f, e;
+};
+
+template <typename T, int NU, int FRONT, int BACK, int LOADER>
+static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
   constexpr int NS = Stages<T>::N;
-  auto kern = rbgs_stream_kernel<T, NU, PROLONG, BACK, LOADER, WARPS, NS, RB>;
-  constexpr size_t smem = (size_t)WARPS * NS * 2 * RB * STRIP * sizeof(T);
+  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, WARPS, NS, RB>;
+  constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0);
+  constexpr size_t smem = (size_t)WARPS * NS * stage_bytes;
   static bool configured[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -27,21 +32,24 @@ static int launch_one(const CUtensorMap& mu, const CUtensorMap& mf, const PassPa
   }
   const int ntiles = (p.nx + p.rows_per_tile - 1) / p.rows_per_tile;
   dim3 grid((p.nstrips + WARPS - 1) / WARPS, ntiles);
-  kern<<<grid, WARPS * 32, smem, st>>>(mu, mf, p, sc);
+  kern<<<grid, WARPS * 32, smem, st>>>(m.u, m.f, m.e, p, sc);
   return 0;
 }
 
 template <typename T, int LOADER>
-int launch_pass(int nu, bool prolong, int back, const CUtensorMap& mu, const CUtensorMap& mf, const PassParams& p,
-                const StencilScalars<T>& sc, cudaStream_t st) {
-#define MG_CASE(NU_, PR_, BK_) \
-  if (nu == NU_ && prolong == PR_ && back == BK_) return launch_one<T, NU_, PR_, BK_, LOADER>(mu, mf, p, sc, st);
-  MG_CASE(0, false, BACK_RESTRICT) MG_CASE(0, false, BACK_NORM)
-  MG_CASE(0, true, BACK_NONE) MG_CASE(0, true, BACK_RESTRICT) MG_CASE(0, true, BACK_NORM)
-  MG_CASE(1, false, BACK_NONE) MG_CASE(1, false, BACK_RESTRICT) MG_CASE(1, false, BACK_NORM)
-  MG_CASE(1, true, BACK_NONE) MG_CASE(1, true, BACK_RESTRICT) MG_CASE(1, true, BACK_NORM)
-  MG_CASE(2, false, BACK_NONE) MG_CASE(2, false, BACK_RESTRICT) MG_CASE(2, false, BACK_NORM)
-  MG_CASE(2, true, BACK_NONE) MG_CASE(2, true, BACK_RESTRICT) MG_CASE(2, true, BACK_NORM)
+int launch_pass(int nu, int front, int back, const Maps& m, const PassParams& p, const StencilScalars<T>& sc,
+                cudaStream_t st) {
+#define MG_CASE(NU_, FR_, BK_) \
+  if (nu == NU_ && front == FR_ && back == BK_) return launch_one<T, NU_, FR_, BK_, LOADER>(m, p, sc, st);
+  MG_CASE(0, FRONT_NONE, BACK_RESTRICT) MG_CASE(0, FRONT_NONE, BACK_NORM)
+  MG_CASE(0, FRONT_PROLONG, BACK_NONE) MG_CASE(0, FRONT_PROLONG, BACK_RESTRICT) MG_CASE(0, FRONT_PROLONG, BACK_NORM)
+  MG_CASE(1, FRONT_NONE, BACK_NONE) MG_CASE(1, FRONT_NONE, BACK_RESTRICT) MG_CASE(1, FRONT_NONE, BACK_NORM)
+  MG_CASE(1, FRONT_PROLONG, BACK_NONE) MG_CASE(1, FRONT_PROLONG, BACK_RESTRICT) MG_CASE(1, FRONT_PROLONG, BACK_NORM)
+  MG_CASE(2, FRONT_NONE, BACK_NONE) MG_CASE(2, FRONT_NONE, BACK_RESTRICT) MG_CASE(2, FRONT_NONE, BACK_NORM)
+  MG_CASE(2, FRONT_PROLONG, BACK_NONE) MG_CASE(2, FRONT_PROLONG, BACK_RESTRICT) MG_CASE(2, FRONT_PROLONG, BACK_NORM)
+  if constexpr (sizeof(T) == 8) {  // mixed-precision defect-correction passes (fp64 iterate, fp32 correction/residual)
+    MG_CASE(0, FRONT_NONE, BACK_RESID) MG_CASE(0, FRONT_ADDFINE, BACK_RESID) MG_CASE(0, FRONT_ADDFINE, BACK_NONE)
+  }
 #undef MG_CASE
   return MG_ERR_UNSUPPORTED;
 }

@@ -203,13 +203,39 @@ def vc_aligned(*fields) -> bool:
     return True
 
 
+class KernelTimer:
+    """Optional CUDA-event timing of individual fused passes inside a running solve (bench.py's roofline
+    leg): events are recorded on the launching stream around every vc_pass on a field of at least
+    `min_points` points; `summary()` synchronises and returns per-kernel launch counts and mean ms."""
+
+    def __init__(self, min_points: int = 0):
+        self.min_points = min_points
+        self.records = []  # (tag, start_event, end_event)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, a, b in self.records:
+            d = out.setdefault(tag, {"launches": 0, "total_ms": 0.0})
+            d["launches"] += 1
+            d["total_ms"] += a.elapsed_time(b)
+        for d in out.values():
+            d["mean_ms"] = d["total_ms"] / d["launches"]
+        return out
+
+
+TIMER: Optional[KernelTimer] = None
+
+
 def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
             sweeps: int = 2, omega: float = 1.0, coefficient: float = -1.0,
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
-            sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0) -> None:
+            sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
+            u_zero: bool = False) -> None:
     """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS sweeps -> [coarse_out = R(f - A u)] or
-    [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored)."""
-    nx, ny = u_in.shape
+    [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored).
+    ``u_zero``: treat u_in as identically zero without reading it."""
+    nx, ny = f.shape
     flags = (rows & 0xFFF) << 8
     if coarse_in is not None:
         flags |= _lib.VC_PROLONG
@@ -219,15 +245,63 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
         flags |= _lib.VC_NORM
     if u_out is None:
         flags |= _lib.VC_NO_STORE
-    if loader == "cp_async":
-        flags |= _lib.VC_LOADER_CPASYNC
-    elif loader != "tma":
-        raise ValueError(f"unknown loader {loader!r}")
-    ws = _vc_workspace(u_in.device, nx, ny) if sumsq_out is not None else None
-    _lib.call("mg_vc_pass", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+    if u_zero:
+        flags |= _lib.VC_U_ZERO
+    flags |= _loader_flag(loader)
+    ws = _vc_workspace(f.device, nx, ny) if sumsq_out is not None else None
+    timed = TIMER is not None and nx * ny >= TIMER.min_points
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.call("mg_vc_pass", None if u_zero else u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None,
+              f.data_ptr(),
               coarse_in.data_ptr() if coarse_in is not None else None,
               coarse_out.data_ptr() if coarse_out is not None else None,
               sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
-              nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
+              nx, ny, 0 if u_zero else ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
               ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
-              hx, hy, omega, coefficient, sweeps, code(u_in.dtype), flags, stream_ptr())
+              hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, stream_ptr())
+    if timed:
+        ev1.record()
+        tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"rbgs{sweeps}"
+               + ("+R" if coarse_out is not None else "") + ("+N" if sumsq_out is not None else "")
+               + f"/{'f64' if f.dtype == torch.float64 else 'f32'}/{nx}x{ny}")
+        TIMER.records.append((tag, ev0, ev1))
+
+
+def _loader_flag(loader: str) -> int:
+    if loader == "cp_async":
+        return _lib.VC_LOADER_CPASYNC
+    if loader != "tma":
+        raise ValueError(f"unknown loader {loader!r}")
+    return 0
+
+
+def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
+                   e_in: Optional[torch.Tensor] = None, r_out: Optional[torch.Tensor] = None,
+                   sumsq_out: Optional[torch.Tensor] = None, coefficient: float = -1.0, loader: str = "tma",
+                   rows: int = 0) -> None:
+    """Mixed-precision defect-correction pass on the fp64 iterate (one HBM pass):
+    u_out = u_in + e_in (fp32 correction; None: u unchanged, nothing stored), r_out = fp32(f - A u_out),
+    sumsq_out[0] = sum of the squared fp64 residual."""
+    nx, ny = u_in.shape
+    if u_in.dtype != torch.float64 or f.dtype != torch.float64:
+        raise TypeError("vc_defect_pass: the iterate and right-hand side are fp64")
+    for t in (e_in, r_out):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("vc_defect_pass: correction and residual are fp32")
+    flags = ((rows & 0xFFF) << 8) | _loader_flag(loader)
+    ws = _vc_workspace(u_in.device, nx, ny) if r_out is not None else None
+    timed = TIMER is not None and nx * ny >= TIMER.min_points
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.call("mg_vc_defect_pass", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+              e_in.data_ptr() if e_in is not None else None, r_out.data_ptr() if r_out is not None else None,
+              sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
+              nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(e_in) if e_in is not None else 0,
+              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, stream_ptr())
+    if timed:
+        ev1.record()
+        TIMER.records.append((("update+" if e_in is not None else "") + ("resid32+N" if r_out is not None else "")
+                              + f"/f64/{nx}x{ny}", ev0, ev1))

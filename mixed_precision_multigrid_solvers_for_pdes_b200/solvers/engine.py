@@ -122,25 +122,30 @@ class CycleEngine:
             return max(1, 2 ** (L - lvl - 2))
         return 0  # reference: unknown cycle strings fall through all branches (multigrid.py:309-319)
 
-    def _cycle_fused(self, level_dtypes, lvl, precision_manager, sumsq_out) -> None:
+    def _cycle_fused(self, level_dtypes, lvl, precision_manager, sumsq_out, u_zero) -> None:
         g = self.levels[lvl].grid
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
         coeff, omega, ld = self.operators[lvl].coefficient, self.smoother.omega, self.loader
         # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
         n = self.pre
+        if u_zero and n == 0:
+            b.u.zero_()  # nothing will overwrite the iterate before it is read
+            u_zero = False
         while n > 2:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero)
             b.u, b.tmp = b.tmp, b.u
             n -= 2
+            u_zero = False
         if n > 0:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld,
+                        u_zero=u_zero)
             b.u, b.tmp = b.tmp, b.u
         else:
             ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld)
-        c.u.zero_()
-        for _ in range(self._reps(lvl)):
-            self.cycle(level_dtypes, lvl + 1, precision_manager)
+        # the coarse error equation starts from e = 0: the first coarse pass is told so instead of reading zeros
+        for rep in range(self._reps(lvl)):
+            self.cycle(level_dtypes, lvl + 1, precision_manager, u_zero=(rep == 0))
         # up: prolongation + correction fused into the first post-smoothing pass, norm into the last
         n = self.post
         first = min(n, 2)
@@ -157,27 +162,32 @@ class CycleEngine:
             b.u, b.tmp = b.tmp, b.u
 
     # -- the recursion ------------------------------------------------------------------------------
-    def cycle(self, level_dtypes: Sequence, lvl: int = 0, precision_manager=None, sumsq_out=None) -> bool:
+    def cycle(self, level_dtypes: Sequence, lvl: int = 0, precision_manager=None, sumsq_out=None,
+              u_zero: bool = False) -> bool:
         """One cycle on level `lvl`, updating that level's ``u`` for ``level_dtypes[lvl]``.
         With ``sumsq_out`` (1 float64 on the device) the fused path also leaves sum((f - A u)^2) of the
-        final iterate there; returns True when it did."""
+        final iterate there; returns True when it did.  ``u_zero``: the iterate of this level is to be
+        taken as zero whatever its buffer holds (the zero initial guess of a coarse error equation)."""
         L = self.num_levels
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         if lvl == L - 1:
+            if u_zero:
+                b.u.zero_()
             self._coarse_solve(lvl, b, precision_manager)
             return False
         if self._fusable(lvl, level_dtypes):
-            self._cycle_fused(level_dtypes, lvl, precision_manager, sumsq_out)
+            self._cycle_fused(level_dtypes, lvl, precision_manager, sumsq_out, u_zero)
             return sumsq_out is not None
+        if u_zero:
+            b.u.zero_()
         if self.pre > 0:
             self._smooth(lvl, b, self.pre)
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
         r = self._residual(lvl, b.u, b.f, b.tmp)
         rop = self.restriction_ops[lvl]
         ops.restrict(r, getattr(rop, "method", "full_weighting"), out=c.f)
-        c.u.zero_()
-        for _ in range(self._reps(lvl)):
-            self.cycle(level_dtypes, lvl + 1, precision_manager)
+        for rep in range(self._reps(lvl)):
+            self.cycle(level_dtypes, lvl + 1, precision_manager, u_zero=(rep == 0))
         pop = self.prolongation_ops[lvl]
         ops.prolong(c.u, getattr(pop, "method", "bilinear"), out=b.u, add=True)
         if self.post > 0:

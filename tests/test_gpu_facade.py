@@ -78,6 +78,9 @@ def test_catalogue_problem_and_errors():
     x = np.linspace(0, 1, 257)
     X, Y = np.meshgrid(x, x, indexing="ij")
     assert info["converged"] and np.max(np.abs(u - pr.analytical_solution(X, Y))) < 2e-6
+    # the reference's all-points norm can never converge when f != 0 on the boundary ring
+    _, strict = MixedPrecisionMultigrid("double", strict_reference_norm=True, max_iterations=12).solve(pr, nx=257, ny=257)
+    assert not strict["converged"] and abs(strict["final_residual"] - 0.0099602384) < 1e-9
     with pytest.raises(ValueError, match="Unknown precision strategy"):
         MixedPrecisionMultigrid("half")
     with pytest.raises(ValueError, match="no CPU path"):

@@ -28,6 +28,7 @@ def _fields(n, m, dt, seed, domain=(0.0, 1.0, 0.0, 1.0)):
 
 def _cmp(got, exp, exact, what, rtol=1e-13):
     got = to_host(got) if isinstance(got, torch.Tensor) else got
+    exp = np.ascontiguousarray(exp)
     assert got.dtype == exp.dtype and got.shape == exp.shape, what
     if exact:
         if not np.array_equal(got, exp):
@@ -150,3 +151,51 @@ def test_large_grid_against_basic_kernels():
         ops.smooth_rbgs_(ref, f, g.hx, g.hy, 1.0, 2)
         assert torch.equal(out, ref)
         assert torch.equal(rc, ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0)))
+
+
+@pytest.mark.parametrize("loader", LOADERS)
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_zero_input_flag(dt, loader):
+    """u_zero: the kernel must behave exactly as if it had read an all-zero iterate (and must not read it)."""
+    n, m = 257, 129
+    _, _, f = _fields(n, m, dt, 12)
+    g = Grid(n, m, dtype=dt)
+    df = to_device(f)[0]
+    zeros = empty_field(n, m, dt)
+    poison = empty_field(n, m, dt)
+    poison.fill_(float("nan"))
+    for sweeps in (1, 2):
+        a, b = empty_field(n, m, dt), empty_field(n, m, dt)
+        ra, rb = empty_field(129, 65, dt), empty_field(129, 65, dt)
+        ops.vc_pass(zeros, a, df, g.hx, g.hy, sweeps=sweeps, coarse_out=ra, loader=loader)
+        ops.vc_pass(poison, b, df, g.hx, g.hy, sweeps=sweeps, coarse_out=rb, loader=loader, u_zero=True)
+        assert torch.equal(a, b) and torch.equal(ra, rb)
+
+
+@pytest.mark.parametrize("loader", LOADERS)
+@pytest.mark.parametrize("n,m", [(129, 129), (257, 65), (33, 1025), (9, 9)])
+def test_defect_pass(n, m, loader):
+    """u_out = u + e32 ; r32 = fp32(f - A u_out) ; sum r^2  -- against the oracle in fp64."""
+    rng = np.random.default_rng(13)
+    g = Grid(n, m)
+    u, f = rng.uniform(-1, 1, (n, m)), rng.uniform(-1, 1, (n, m))
+    e = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    du, df, de = to_device(u)[0], to_device(f)[0], to_device(e)[0]
+    uo = empty_field(n, m, np.float64)
+    r32 = empty_field(n, m, np.float32)
+    ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ops.vc_defect_pass(du, uo, df, g.hx, g.hy, e_in=de, r_out=r32, sumsq_out=ss, loader=loader)
+    un = u + e.astype(np.float64)
+    assert np.array_equal(to_host(uo), un)
+    r = O.residual(un, f, g.hx, g.hy, -1.0)
+    exact = n == m
+    _cmp(r32, r.astype(np.float32), exact, f"defect residual {n}x{m} {loader}", rtol=1e-13)
+    assert abs(ss.item() - np.sum(r ** 2)) <= 1e-12 * np.sum(r ** 2)
+    # residual only (no correction): nothing stored, same residual of the unchanged iterate
+    r32b = empty_field(n, m, np.float32)
+    ops.vc_defect_pass(du, None, df, g.hx, g.hy, r_out=r32b, sumsq_out=ss, loader=loader)
+    _cmp(r32b, O.residual(u, f, g.hx, g.hy, -1.0).astype(np.float32), exact, "residual only")
+    # update only
+    uo2 = empty_field(n, m, np.float64)
+    ops.vc_defect_pass(du, uo2, df, g.hx, g.hy, e_in=de, loader=loader)
+    assert torch.equal(uo2, uo)

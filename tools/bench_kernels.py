@@ -11,7 +11,12 @@ from mixed_precision_multigrid_solvers_for_pdes_b200 import ops  # noqa: E402
 from mixed_precision_multigrid_solvers_for_pdes_b200.device import empty_field  # noqa: E402
 
 
-def timeit(fn, iters=5, warm=2):
+ITERS, WARM = 5, 2
+
+
+def timeit(fn, iters=None, warm=None):
+    iters = ITERS if iters is None else iters
+    warm = WARM if warm is None else warm
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -32,7 +37,11 @@ def main():
     ap.add_argument("--loaders", default="tma,cp_async")
     ap.add_argument("--rows", default="0")
     ap.add_argument("--modes", default="smooth2,smooth1,down2,up2,up2norm,resrestrict")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--warm", type=int, default=2)
     a = ap.parse_args()
+    global ITERS, WARM
+    ITERS, WARM = a.iters, a.warm
     n = a.n
     h = 1.0 / (n - 1)
     nc = (n - 1) // 2 + 1
