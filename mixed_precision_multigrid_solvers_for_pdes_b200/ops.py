@@ -15,7 +15,9 @@ _ws: Dict[Tuple[int, int], torch.Tensor] = {}
 
 def _workspace(dev: torch.device) -> torch.Tensor:
     """Per-(device, stream) reduction scratch: partials followed by 8 result slots."""
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr())
+    # one scratch per device: launches are stream-ordered and the package drives one stream per device
+    # (a capturing stream replays in the same order), so the buffer is never used concurrently
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), 0)
     w = _ws.get(key)
     if w is None:
         n = _lib.call("mg_sumsq_workspace_doubles")
@@ -184,7 +186,7 @@ _vc_ws: Dict[Tuple[int, int], torch.Tensor] = {}
 
 def _vc_workspace(dev: torch.device, nx: int, ny: int) -> torch.Tensor:
     need = _lib.call("mg_vc_workspace_doubles", nx, ny)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream_ptr())
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), 0)
     w = _vc_ws.get(key)
     if w is None or w.numel() < need:
         w = torch.zeros(need, dtype=torch.float64, device=dev)

@@ -59,6 +59,20 @@ class CycleEngine:
         self.loader = loader
         self.coarse_info = torch.zeros(2, dtype=torch.float64, device=self.dev)
 
+    # -- buffer roles (u / tmp swap on every out-of-place pass) ---------------------------------------
+    def buffer_state(self):
+        """Which physical buffer currently plays `u` on every (level, dtype): the key of a captured graph."""
+        return tuple((li, str(dt), b.u.data_ptr()) for li, lv in enumerate(self.levels)
+                     for dt, b in sorted(lv._bufs.items(), key=lambda kv: str(kv[0])))
+
+    def snapshot_roles(self):
+        return [(b, b.u, b.tmp) for lv in self.levels for b in lv._bufs.values()]
+
+    @staticmethod
+    def restore_roles(snap) -> None:
+        for b, u, tmp in snap:
+            b.u, b.tmp = u, tmp
+
     # -- per-level building blocks ----------------------------------------------------------------
     @property
     def num_levels(self) -> int:

@@ -57,7 +57,7 @@ class MixedPrecisionMultigrid:
                  stagnation_ratio: float = 0.95, max_grid_size: Optional[int] = None,
                  gpu_memory_fraction: Optional[float] = None, min_precision: Optional[str] = None,
                  strict_reference_norm: bool = False, kernels: str = "auto", loader: str = "tma", device=None,
-                 verbose: bool = False):
+                 use_cuda_graphs: bool = True, verbose: bool = False):
         key = str(precision_strategy).lower()
         if key not in _STRATEGIES:
             raise ValueError(f"Unknown precision strategy: {precision_strategy}")
@@ -82,6 +82,10 @@ class MixedPrecisionMultigrid:
         # meet the tolerance although those values enter no equation.  Unless the strict
         # behaviour is requested, the ring of f is zeroed so the test measures the interior residual.
         self.strict_reference_norm = strict_reference_norm
+        # One multigrid cycle is ~3 launches per level, most of them microseconds long on the coarse levels:
+        # each (phase, buffer-role state) is captured once into a CUDA graph and replayed afterwards.
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs: Dict[Any, Any] = {}
         self.enable_precision_monitoring = False
         self.precision_switches: List[Dict[str, Any]] = []
         self._engine: Optional[CycleEngine] = None
@@ -132,22 +136,53 @@ class MixedPrecisionMultigrid:
         self._shape, self._domain, self._grid = (nx, ny), tuple(domain), g
         self._sumsq = torch.zeros(2, dtype=torch.float64, device=dev)
         self._pinned_out = None
+        self._graphs = {}
         # fp64 iterate / rhs of the refinement phase live in the engine's fp64 level-0 buffers
 
-    # -- one cycle in each precision phase -----------------------------------------------------------------
-    def _cycle_fp64(self) -> float:
+    # -- CUDA-graph replay of one step -----------------------------------------------------------------------
+    def _graphed(self, name: str, launch) -> None:
+        """Run `launch()` (a fixed sequence of kernel launches writing its norm into self._sumsq[2]) through a
+        CUDA graph captured per (step kind, buffer-role state).  The first use of a state runs eagerly (it
+        also warms every lazily allocated workspace), the second captures, later ones replay."""
         eng = self._engine
-        L = eng.num_levels
-        fused = eng.cycle([torch.float64] * L, 0, None, sumsq_out=self._sumsq[0:1])
-        ss = self._sumsq[0:1] if fused else eng.residual_sumsq_async(torch.float64)
+        if not self.use_cuda_graphs:
+            launch()
+            return
+        key = (name, eng.buffer_state())
+        entry = self._graphs.get(key)
+        if entry is None:  # first visit: eager
+            launch()
+            self._graphs[key] = "warm"
+            return
+        if entry == "warm":  # second visit: capture (capture does not execute), then fall through to replay
+            before = eng.snapshot_roles()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+            after = eng.snapshot_roles()
+            eng.restore_roles(before)
+            entry = self._graphs[key] = (g, after)
+        g, after = entry
+        g.replay()
+        eng.restore_roles(after)
+
+    def _norm_from(self, ss: torch.Tensor) -> float:
         return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))
 
-    def _cycle_fp32_only(self) -> float:
+    # -- one cycle in each precision phase -----------------------------------------------------------------
+    def _launch_uniform_cycle(self, dtype) -> None:
         eng = self._engine
-        L = eng.num_levels
-        fused = eng.cycle([torch.float32] * L, 0, None, sumsq_out=self._sumsq[0:1])
-        ss = self._sumsq[0:1] if fused else eng.residual_sumsq_async(torch.float32)
-        return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))
+        fused = eng.cycle([dtype] * eng.num_levels, 0, None, sumsq_out=self._sumsq[0:1])
+        if not fused:
+            self._sumsq[0:1].copy_(eng.residual_sumsq_async(dtype))
+
+    def _cycle_fp64(self) -> float:
+        self._graphed("fp64", lambda: self._launch_uniform_cycle(torch.float64))
+        return self._norm_from(self._sumsq[0:1])
+
+    def _cycle_fp32_only(self) -> float:
+        self._graphed("fp32", lambda: self._launch_uniform_cycle(torch.float32))
+        return self._norm_from(self._sumsq[0:1])
 
     def _inner_dtypes(self):
         """fp32 on every level except the coarsest, which stays fp64 like the reference's per-level
@@ -158,6 +193,10 @@ class MixedPrecisionMultigrid:
 
     def _refinement_residual(self, with_update: bool = False) -> float:
         """One HBM pass over the fp64 iterate: [u += e32] ; r32 = fp32(f - A u) ; fp64 h-scaled ||r||."""
+        self._launch_refinement_residual(with_update)
+        return self._norm_from(self._sumsq[1:2])
+
+    def _launch_refinement_residual(self, with_update: bool) -> None:
         eng, g = self._engine, self._grid
         b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)
         ss = self._sumsq[1:2]
@@ -172,14 +211,17 @@ class MixedPrecisionMultigrid:
             if with_update:
                 ops.axpy_(1.0, b32.u, b64.u)
             ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp)
-            ss = ops.sumsq_async(b64.tmp, slot=1)
+            ss.copy_(ops.sumsq_async(b64.tmp, slot=1))
             ops.cast(b64.tmp, torch.float32, out=b32.f)
-        return float(np.sqrt(g.hx * g.hy * ss.item()))
+
+    def _launch_refinement_cycle(self) -> None:
+        self._engine.cycle(self._inner_dtypes(), 0, None, u_zero=True)
+        self._launch_refinement_residual(True)
 
     def _cycle_refinement(self) -> float:
         """One fp32 cycle on A e = r32 (e0 = 0, never read), then u64 += e32 fused with the next residual."""
-        self._engine.cycle(self._inner_dtypes(), 0, None, u_zero=True)
-        return self._refinement_residual(with_update=True)
+        self._graphed("refine", self._launch_refinement_cycle)
+        return self._norm_from(self._sumsq[1:2])
 
     # -- public API ------------------------------------------------------------------------------------------
     def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None

@@ -102,3 +102,16 @@ def test_large_grid_mixed_reaches_discretisation_accuracy():
     err = ops.maxerr_sinsin(to_device(u)[0])
     # the algebraic error left at ||r|| < 1e-8 is ~1e-10: within 1% of 4.9023e-8
     assert abs(err - O.mms_discretisation_error(n)) <= 0.01 * O.mms_discretisation_error(n)
+
+
+@pytest.mark.parametrize("strategy", ["adaptive", "double", "refinement"])
+def test_cuda_graph_replay_is_bitwise_identical_to_eager(strategy):
+    p = PoissonProblem(source_term, nx=513, ny=513)
+    ue, ie = MixedPrecisionMultigrid(strategy, use_cuda_graphs=False).solve(p)
+    sg = MixedPrecisionMultigrid(strategy, use_cuda_graphs=True)
+    ug, ig = sg.solve(p)
+    ug = ug.copy()
+    ug2, ig2 = sg.solve(p)  # second solve: every step replays a captured graph
+    assert ie["residual_history"] == ig["residual_history"] == ig2["residual_history"]
+    assert np.array_equal(ue, ug) and np.array_equal(ue, ug2)
+    assert any(isinstance(v, tuple) for v in sg._graphs.values())
