@@ -196,6 +196,21 @@ MG_API int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const
                       int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy, double coefficient,
                       int flags, void* stream);
 
+/* Row-slab variants for the 1-D domain decomposition over GPUs (the reference's strip decomposition,
+ * gpu/multi_gpu_solver.py:347-383): the field handed in is a slab of rows of a larger grid including its
+ * ghost rows; the first / last local rows are treated like Dirichlet rows (they are ghost rows refreshed by
+ * the halo exchange, or true boundary rows on the first / last rank).  nx may be even.  Only rows
+ * [norm_row_lo, norm_row_hi) enter the residual sum (each rank sums the rows it owns; hi < 0: all). */
+MG_API int mg_vc_pass_slab(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
+                    double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
+                    int64_t ld_f, int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega,
+                    double coefficient, int sweeps, int dtype, int flags, int norm_row_lo, int norm_row_hi,
+                    void* stream);
+MG_API int mg_vc_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
+                           double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in,
+                           int64_t ld_out, int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy,
+                           double coefficient, int flags, int norm_row_lo, int norm_row_hi, void* stream);
+
 /* `sweeps` temporally blocked RB-GS sweeps in one HBM pass (replaces GaussSeidelSmoother(red_black=True)
  * .smooth, smoothers.py:117-151; SmoothingKernels.red_black_gauss_seidel / block_gauss_seidel_kernel,
  * gpu/cuda_kernels.py:348-390, 982-1048). */

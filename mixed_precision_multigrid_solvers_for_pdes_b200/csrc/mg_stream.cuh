@@ -65,6 +65,7 @@ struct PassParams {
   int nx, ny, nxc, nyc;
   int64_t ld_in, ld_out, ld_f, ld_ci, ld_co, ld_fi, ld_ro;
   int u_zero;              // 1: u_in is identically zero and is not read
+  int norm_row_lo, norm_row_hi;  // rows [lo, hi) entering the residual sum (a slab sums only the rows it owns)
   int rows_per_tile;       // R (even)
   int nstrips;
   int store_u;             // 0: do not write u_out (pure residual passes)
@@ -448,10 +449,12 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
         if (HAS_NORM) {
           if (q2 >= I0 && q2 < I1) {
+            if (q2 >= p.norm_row_lo && q2 < p.norm_row_hi) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const T sq = r[e] * r[e];  // squared in T like NumPy's field**2, accumulated in fp64
-              acc += ((own >> e) & 1u) ? (double)sq : 0.0;
+              for (int e = 0; e < 4; ++e) {
+                const T sq = r[e] * r[e];  // squared in T like NumPy's field**2, accumulated in fp64
+                acc += ((own >> e) & 1u) ? (double)sq : 0.0;
+              }
             }
             if (BACK == BACK_RESID && own != 0u) {
               float* dst = p.resid_out + (int64_t)q2 * p.ld_ro + jbase;

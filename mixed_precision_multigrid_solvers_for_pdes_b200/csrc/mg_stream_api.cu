@@ -69,7 +69,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
                     const float* fine_in, float* resid_out, double* sumsq_out, double* workspace, int nx, int ny,
                     int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_ci, int64_t ld_co, int64_t ld_fi,
                     int64_t ld_ro, double hx, double hy, double omega, double coefficient, int sweeps, int dtype,
-                    int front, int back, int flags, void* stream, const char* what) {
+                    int front, int back, int flags, void* stream, const char* what, int norm_lo = 0,
+                    int norm_hi = -1) {
   const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
   const bool store = (flags & MG_VC_NO_STORE) == 0;
   const bool u_zero = (flags & MG_VC_U_ZERO) != 0;
@@ -83,7 +84,9 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   if (sweeps == 0 && front == FRONT_NONE && back == BACK_NONE) return MG_ERR_BADARG;
   const int nxc = (nx - 1) / 2 + 1, nyc = (ny - 1) / 2 + 1;
   if (front == FRONT_PROLONG || back == BACK_RESTRICT) {
-    if ((nx - 1) % 2 || (ny - 1) % 2) return MG_ERR_BADARG;
+    // ny must be odd.  An even nx is accepted: it is a row slab of a larger grid whose last local row is a ghost
+    // row (coarse local row ic <-> fine local row 2ic, ic <= (nx-1)/2).
+    if ((ny - 1) % 2) return MG_ERR_BADARG;
     if (front == FRONT_PROLONG && (!coarse_in || ld_ci < nyc)) return MG_ERR_BADARG;
     if (back == BACK_RESTRICT && (!coarse_out || ld_co < nyc)) return MG_ERR_BADARG;
   }
@@ -111,6 +114,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   p.ld_in = u_zero ? ld_f : ld_in; p.ld_out = ld_out; p.ld_f = ld_f; p.ld_ci = ld_ci; p.ld_co = ld_co;
   p.ld_fi = ld_fi; p.ld_ro = ld_ro;
   p.u_zero = u_zero ? 1 : 0;
+  p.norm_row_lo = norm_lo < 0 ? 0 : norm_lo;
+  p.norm_row_hi = (norm_hi < 0 || norm_hi > nx) ? nx : norm_hi;
   p.nstrips = num_strips(ny, sweeps, back);
   p.rows_per_tile = pick_rows(nx, p.nstrips, rows_override);
   p.store_u = store ? 1 : 0;
@@ -161,6 +166,31 @@ int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* coarse_
   return run_pass(u_in, u_out, f, coarse_in, coarse_out, nullptr, nullptr, sumsq_out, workspace, nx, ny, ld_in, ld_out,
                   ld_f, ld_ci, ld_co, 0, 0, hx, hy, omega, coefficient, sweeps, dtype, front, back, flags, stream,
                   "mg_vc_pass");
+}
+
+int mg_vc_pass_slab(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
+                    double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
+                    int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega, double coefficient, int sweeps,
+                    int dtype, int flags, int norm_row_lo, int norm_row_hi, void* stream) {
+  if ((flags & MG_VC_RESTRICT) && (flags & MG_VC_NORM)) return MG_ERR_UNSUPPORTED;
+  const int front = (flags & MG_VC_PROLONG) ? FRONT_PROLONG : FRONT_NONE;
+  const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
+  return run_pass(u_in, u_out, f, coarse_in, coarse_out, nullptr, nullptr, sumsq_out, workspace, nx, ny, ld_in, ld_out,
+                  ld_f, ld_ci, ld_co, 0, 0, hx, hy, omega, coefficient, sweeps, dtype, front, back, flags, stream,
+                  "mg_vc_pass_slab", norm_row_lo, norm_row_hi);
+}
+
+int mg_vc_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
+                           double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
+                           int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy, double coefficient, int flags,
+                           int norm_row_lo, int norm_row_hi, void* stream) {
+  const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
+  const int back = r_out ? BACK_RESID : BACK_NONE;
+  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_U_ZERO);
+  if (!e_in) fl |= MG_VC_NO_STORE;
+  return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
+                  workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,
+                  back, fl, stream, "mg_vc_defect_pass_slab", norm_row_lo, norm_row_hi);
 }
 
 int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out, double* sumsq_out,

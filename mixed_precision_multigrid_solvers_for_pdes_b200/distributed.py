@@ -1,0 +1,605 @@
+"""Row-slab domain decomposition of the multigrid cycle over the GPUs of one box.
+
+One process per GPU (torchrun).  The fine levels are partitioned into contiguous slabs of rows
+(first index; rows are contiguous in memory, so halo rows are contiguous messages); every slab carries
+GHOST = 8 ghost rows per interior side on EVERY distributed level.  The same fused kernels as on one GPU
+run on the slab (`mg_vc_pass_slab`): a pass with 2 RB-GS sweeps and a residual/restriction stage has a
+dependency cone of 6 rows, so after a pass the owned rows are exact while the outer ghost rows are stale;
+they are refreshed by ONE grouped NCCL send/recv pair per neighbour per pass output (temporal blocking
+means one exchange per 2 sweeps instead of one per colour half-sweep).  Ownership is aligned to powers
+of two so every coarse row has a unique owner and the transfers need no extra communication.
+
+Below `agglomerate_below` fine points per side the remaining levels are AGGLOMERATED: the owned rows of
+the coarse right-hand side are all-gathered and every rank runs the remaining sub-cycle redundantly on the
+full (small) grid — identical results on all ranks, no broadcast back, no idle GPUs — then copies its slab
+(including ghosts) out of the full correction.  The residual norm is one NCCL all-reduce of one double per
+cycle.  Reference counterpart: gpu/multi_gpu_solver.py:90-185, 244-383 (strip decomposition, peer copies,
+host-side sum; no coarse levels) — a design sketch, not an algorithm.
+
+Results on owned rows are bit-identical to the single-GPU run (RB-GS is order independent within a
+colour); only the norm reduction order differs (1e-15 relative)."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+GHOST = 8  # ghost rows per interior side on every distributed level (even; >= 6 = cone of a fused pass)
+
+
+# ======================================================================================================
+# Partition (pure host logic)
+# ======================================================================================================
+@dataclass
+class SlabLevel:
+    level: int
+    nx_glob: int
+    ny: int
+    hx: float
+    hy: float
+    own_lo: int      # global rows owned: [own_lo, own_hi)
+    own_hi: int
+    g_lo: int        # ghost rows present below / above (0 on a physical boundary)
+    g_hi: int
+
+    @property
+    def row0(self) -> int:           # global row of local row 0
+        return self.own_lo - self.g_lo
+
+    @property
+    def loc_nx(self) -> int:
+        return (self.own_hi - self.own_lo) + self.g_lo + self.g_hi
+
+    @property
+    def own_local(self) -> Tuple[int, int]:
+        return (self.g_lo, self.g_lo + (self.own_hi - self.own_lo))
+
+
+class SlabPartition:
+    """Ownership of global rows per level for `world` ranks; levels [0, dist_levels) are distributed."""
+
+    def __init__(self, nx: int, ny: int, world: int, rank: int, num_levels: int, dist_levels: int,
+                 domain=(0.0, 1.0, 0.0, 1.0), ghost: int = GHOST):
+        if world < 1 or not (0 <= rank < world):
+            raise ValueError("bad world/rank")
+        if dist_levels < 1 or dist_levels > num_levels:
+            raise ValueError("dist_levels must be in [1, num_levels]")
+        if (nx - 1) % (world * 2 ** (dist_levels - 1)) != 0:
+            raise ValueError(f"(nx-1)={nx - 1} must be a multiple of world*2^(dist_levels-1) = {world * 2 ** (dist_levels - 1)}")
+        self.world, self.rank, self.ghost = world, rank, ghost
+        self.num_levels, self.dist_levels = num_levels, dist_levels
+        self.levels: List[SlabLevel] = []
+        n, m = nx, ny
+        hx = (domain[1] - domain[0]) / (nx - 1)
+        hy = (domain[3] - domain[2]) / (ny - 1)
+        for l in range(dist_levels):
+            per = (n - 1) // world
+            if world > 1 and per < ghost:
+                raise ValueError(f"level {l}: {per} rows per rank < ghost depth {ghost}; lower dist_levels")
+            lo, hi = rank * per, (rank + 1) * per + (1 if rank == world - 1 else 0)
+            self.levels.append(SlabLevel(l, n, m, hx, hy, lo, hi, 0 if rank == 0 else ghost,
+                                         0 if rank == world - 1 else ghost))
+            n, m, hx, hy = (n - 1) // 2 + 1, (m - 1) // 2 + 1, hx * 2, hy * 2
+        self.agg_shape = (n, m) if dist_levels < num_levels else None  # global grid of the first agglomerated level
+        self.agg_h = (hx, hy)
+        # rows of the agglomerated level this rank copies back into its level-(D-1)-coarse buffer
+        if self.agg_shape is not None:
+            per = (n - 1) // world
+            lo, hi = rank * per, (rank + 1) * per + (1 if rank == world - 1 else 0)
+            self.agg_slab = SlabLevel(dist_levels, n, m, hx, hy, lo, hi, 0 if rank == 0 else min(ghost, lo),
+                                      0 if rank == world - 1 else min(ghost, n - hi))
+        else:
+            self.agg_slab = None
+
+    def slab(self, l: int) -> SlabLevel:
+        return self.levels[l] if l < self.dist_levels else self.agg_slab
+
+    def coarse_view(self, l: int) -> Tuple[int, int]:
+        """(offset, rows) of the window of level l+1's LOCAL array that lines up with level l's local rows
+        (coarse local row ic <-> fine local row 2ic)."""
+        f, c = self.slab(l), self.slab(l + 1)
+        off = f.row0 // 2 - c.row0
+        rows = (f.loc_nx - 1) // 2 + 1
+        assert f.row0 % 2 == 0 and off >= 0 and off + rows <= c.loc_nx, (f, c, off, rows)
+        return off, rows
+
+
+def choose_dist_levels(nx: int, ny: int, world: int, num_levels: int, agglomerate_below: int = 1025,
+                       ghost: int = GHOST) -> int:
+    """Distribute level l while its grid has more than `agglomerate_below` points per side and every rank
+    owns at least 4*ghost rows with power-of-two aligned slab boundaries."""
+    d = 0
+    n, m = nx, ny
+    for l in range(num_levels):
+        per = (n - 1) // world
+        ok = (n - 1) % world == 0 and per >= 4 * ghost and (nx - 1) % (world * 2 ** l) == 0
+        if l > 0 and min(n, m) <= agglomerate_below:
+            ok = False
+        if not ok:
+            break
+        d = l + 1
+        n, m = (n - 1) // 2 + 1, (m - 1) // 2 + 1
+    return max(1, min(d, num_levels))
+
+
+# ======================================================================================================
+# Local compute back ends
+# ======================================================================================================
+class DeviceBackend:
+    """Production back end: libmgb200 kernels on pitched CUDA tensors."""
+
+    def __init__(self, device, loader: str = "tma"):
+        from . import ops
+        from .device import empty_field
+        self.ops, self._empty, self.device, self.loader = ops, empty_field, device, loader
+
+    def empty(self, nx, ny, dtype):
+        return self._empty(nx, ny, dtype, self.device)
+
+    def scalar(self, n=1):
+        return torch.zeros(n, dtype=torch.float64, device=self.device)
+
+    def vc_pass(self, *a, **k):
+        return self.ops.vc_pass(*a, loader=self.loader, **k)
+
+    def vc_defect_pass(self, *a, **k):
+        return self.ops.vc_defect_pass(*a, loader=self.loader, **k)
+
+    def make_coarse_engine(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max):
+        from .core.grid import Grid
+        from .operators.laplacian import LaplacianOperator
+        from .operators.transfer import ProlongationOperator, RestrictionOperator
+        from .solvers.engine import CycleEngine
+        from .solvers.smoothers import GaussSeidelSmoother
+        grids = [Grid(nx, ny, domain)]
+        for _ in range(1, levels):
+            grids.append(grids[-1].coarsen())
+        L = len(grids)
+        op = LaplacianOperator(-1.0)
+        eng = CycleEngine(grids, smoother=GaussSeidelSmoother(red_black=True),
+                          coarse_solver=GaussSeidelSmoother(max_iterations=coarse_max, tolerance=coarse_tol),
+                          operators=[op] * L, restriction_ops=[RestrictionOperator()] * max(0, L - 1),
+                          prolongation_ops=[ProlongationOperator()] * max(0, L - 1), cycle_type=cycle_type, pre=pre,
+                          post=post, kernels="auto", loader=self.loader, device=self.device)
+        return _DeviceCoarse(eng)
+
+
+class _DeviceCoarse:
+    def __init__(self, eng):
+        self.eng = eng
+        self.L = eng.num_levels
+
+    def dtypes(self, dtype):
+        # the coarsest level stays fp64 (reference: never converted, multigrid.py:270-272)
+        return [dtype] * (self.L - 1) + [torch.float64] if self.L > 1 else [torch.float64]
+
+    def bufs(self, dtype):
+        return self.eng.levels[0].bufs(self.dtypes(dtype)[0])
+
+    def cycle(self, dtype, u_zero: bool):
+        self.eng.cycle(self.dtypes(dtype), 0, None, u_zero=u_zero)
+        return self.bufs(dtype).u
+
+
+# ======================================================================================================
+# Distributed cycle engine
+# ======================================================================================================
+class _Bufs:
+    __slots__ = ("u", "tmp", "f")
+
+
+class DistributedCycleEngine:
+    def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), num_levels: Optional[int] = None,
+                 cycle_type: str = "V", pre: int = 2, post: int = 2, agglomerate_below: int = 1025,
+                 dist_levels: Optional[int] = None, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
+                 backend=None, group=None, device=None):
+        if not (1 <= pre <= 2 and 1 <= post <= 2):
+            raise ValueError("the distributed engine runs 1 or 2 pre/post sweeps per pass")
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nx, self.ny, self.domain = nx, ny, tuple(domain)
+        self.cycle_type, self.pre, self.post = cycle_type, pre, post
+        if num_levels is None:
+            num_levels, a, b = 1, nx, ny
+            while (a - 1) % 2 == 0 and (b - 1) % 2 == 0 and (a - 1) // 2 + 1 >= 5 and (b - 1) // 2 + 1 >= 5:
+                a, b, num_levels = (a - 1) // 2 + 1, (b - 1) // 2 + 1, num_levels + 1
+        self.num_levels = num_levels
+        if dist_levels is None:
+            dist_levels = choose_dist_levels(nx, ny, self.world, num_levels, agglomerate_below)
+        if dist_levels >= num_levels:
+            dist_levels = num_levels - 1  # the coarsest level is always solved on the gathered grid
+        self.part = SlabPartition(nx, ny, self.world, self.rank, num_levels, max(1, dist_levels), domain)
+        self.D = self.part.dist_levels
+        self.be = backend if backend is not None else DeviceBackend(device)
+        self._bufs: Dict[Tuple[int, torch.dtype], _Bufs] = {}
+        an, am = self.part.agg_shape
+        self.coarse = self.be.make_coarse_engine(an, am, self.domain, num_levels - self.D, cycle_type, pre, post,
+                                                 coarse_tolerance, coarse_max_iterations)
+        self.exchanges = 0
+
+    # -- buffers ------------------------------------------------------------------------------------------
+    def bufs(self, l: int, dtype) -> _Bufs:
+        key = (l, dtype)
+        b = self._bufs.get(key)
+        if b is None:
+            s = self.part.slab(l)
+            b = _Bufs()
+            b.u, b.tmp, b.f = (self.be.empty(s.loc_nx, s.ny, dtype) for _ in range(3))
+            self._bufs[key] = b
+        return b
+
+    # -- communication ------------------------------------------------------------------------------------
+    def exchange(self, t: torch.Tensor, l: int) -> None:
+        """Refresh the ghost rows of a level-l local array from the neighbouring slabs."""
+        if self.world == 1:
+            return
+        s = self.part.slab(l)
+        G = self.part.ghost
+        lo, hi = s.own_local
+        ops_ = []
+        keep = []
+        if s.g_lo:  # lower neighbour (rank - 1)
+            send = t[lo:lo + G].contiguous() if not _rows_contiguous(t) else _rows(t, lo, lo + G)
+            recv = _rows(t, 0, s.g_lo) if _rows_contiguous(t) else torch.empty_like(t[0:s.g_lo])
+            ops_ += [dist.P2POp(dist.isend, send, self._peer(self.rank - 1), self.group),
+                     dist.P2POp(dist.irecv, recv, self._peer(self.rank - 1), self.group)]
+            keep.append((recv, 0, s.g_lo))
+        if s.g_hi:  # upper neighbour (rank + 1)
+            send = t[hi - G:hi].contiguous() if not _rows_contiguous(t) else _rows(t, hi - G, hi)
+            recv = _rows(t, hi, hi + s.g_hi) if _rows_contiguous(t) else torch.empty_like(t[hi:hi + s.g_hi])
+            ops_ += [dist.P2POp(dist.isend, send, self._peer(self.rank + 1), self.group),
+                     dist.P2POp(dist.irecv, recv, self._peer(self.rank + 1), self.group)]
+            keep.append((recv, hi, hi + s.g_hi))
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+        if not _rows_contiguous(t):
+            for recv, a, b in keep:
+                t[a:b].copy_(recv)
+        self.exchanges += 1
+
+    def _peer(self, r: int) -> int:
+        return r if self.group is None else dist.get_global_rank(self.group, r)
+
+    def allreduce_sum(self, x: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+        return x
+
+    # -- agglomerated levels --------------------------------------------------------------------------------
+    def _agglomerated_cycle(self, dtype, u_zero: bool) -> None:
+        """Level D: gather the owned rows of the local right-hand side into the full grid on every rank,
+        run the remaining sub-cycle redundantly, copy the local slab (with ghosts) of the correction back."""
+        s = self.part.agg_slab
+        b = self.bufs(self.D, dtype)
+        cb = self.coarse.bufs(dtype)
+        lo, hi = s.own_local
+        per = (s.nx_glob - 1) // self.world
+        if u_zero:  # first visit in this cycle: the right-hand side is new
+            if self.world == 1:
+                cb.f.copy_(b.f)
+            else:
+                # every rank contributes rows [own_lo, own_lo + per]: `per` owned rows plus one more (the boundary
+                # row on the last rank; elsewhere a ghost row that is ignored below)
+                mine = _pitched_rows(b.f, lo, lo + per + 1).contiguous()
+                chunks = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(chunks, mine, group=self.group)
+                ny = s.ny
+                for p in range(self.world):
+                    cb.f[p * per:(p + 1) * per].copy_(chunks[p][:per, :ny])
+                cb.f[self.world * per].copy_(chunks[self.world - 1][per, :ny])
+        full_u = self.coarse.cycle(dtype, u_zero)
+        b.u.copy_(full_u[s.row0:s.row0 + s.loc_nx])
+
+    # -- the recursion ----------------------------------------------------------------------------------------
+    def _reps(self, l: int) -> int:
+        if self.cycle_type == "V":
+            return 1
+        if self.cycle_type == "W":
+            return 2
+        if self.cycle_type == "F":
+            return max(1, 2 ** (self.num_levels - l - 2))
+        return 0
+
+    def cycle(self, dtype, l: int = 0, u_zero: bool = False, sumsq_out: Optional[torch.Tensor] = None) -> None:
+        """One cycle on distributed level l (all distributed levels in `dtype`)."""
+        if l == self.D:
+            self._agglomerated_cycle(dtype, u_zero)
+            return
+        s = self.part.slab(l)
+        b, c = self.bufs(l, dtype), self.bufs(l + 1, dtype)
+        off, rows = self.part.coarse_view(l)
+        self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.pre, coefficient=-1.0, coarse_out=c.f[off:off + rows],
+                        u_zero=u_zero)
+        b.u, b.tmp = b.tmp, b.u
+        self.exchange(b.u, l)
+        if l + 1 < self.D:
+            self.exchange(c.f, l + 1)  # the agglomerated level gathers owned rows only
+        for rep in range(self._reps(l)):
+            self.cycle(dtype, l + 1, u_zero=(rep == 0))
+        self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.post, coefficient=-1.0, coarse_in=c.u[off:off + rows],
+                        sumsq_out=sumsq_out if l == 0 else None, norm_rows=s.own_local)
+        b.u, b.tmp = b.tmp, b.u
+        self.exchange(b.u, l)
+
+    # -- data movement helpers -----------------------------------------------------------------------------------
+    def scatter_rows(self, dst: torch.Tensor, full_rows_fn, l: int = 0) -> None:
+        """Fill a level-l local array (owned + ghost rows) from a function global_row_range -> tensor."""
+        s = self.part.slab(l)
+        dst.copy_(full_rows_fn(s.row0, s.row0 + s.loc_nx))
+
+    def gather_solution(self, local_u: torch.Tensor, l: int = 0) -> Optional[torch.Tensor]:
+        """All ranks -> the full (nx_glob, ny) field on every rank (tests / small grids only)."""
+        s = self.part.slab(l)
+        lo, hi = s.own_local
+        if self.world == 1:
+            return local_u[lo:hi].clone()
+        per = (s.nx_glob - 1) // self.world
+        mine = local_u[lo:lo + per + 1].contiguous() if self.rank == self.world - 1 else torch.cat(
+            [local_u[lo:lo + per], local_u[lo + per:lo + per + 1]]).contiguous()
+        out = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return torch.cat([o[:per] for o in out] + [out[-1][per:per + 1]])
+
+
+def _rows_contiguous(t: torch.Tensor) -> bool:
+    # a pitched field: rows of `ld` elements back to back; a block of rows is one contiguous memory range
+    return t.stride(1) == 1
+
+
+def _rows(t: torch.Tensor, a: int, b: int) -> torch.Tensor:
+    """Rows [a, b) of a pitched field INCLUDING the row padding, as one contiguous 1-D tensor (a single message)."""
+    ldp = t.stride(0)
+    return torch.as_strided(t, ((b - a) * ldp,), (1,), t.storage_offset() + a * ldp)
+
+
+def _pitched_rows(t: torch.Tensor, a: int, b: int) -> torch.Tensor:
+    ldp = t.stride(0)
+    return torch.as_strided(t, (b - a, ldp), (ldp, 1), t.storage_offset() + a * ldp)
+
+
+# ======================================================================================================
+# Mixed-precision driver on the distributed engine (same phases as solvers/mixed_precision.py)
+# ======================================================================================================
+class DistributedMixedPrecisionSolver:
+    """fp32-cycle / fp64-residual refinement with a switch to fp64 cycles, on row slabs.
+    `step()` runs one cycle of the solve loop and returns the global h-scaled residual norm."""
+
+    def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), precision_strategy: str = "adaptive",
+                 switch_threshold: float = 1e-6, tolerance: float = 1e-8, max_iterations: int = 50, backend=None,
+                 device=None, **engine_kw):
+        self.eng = DistributedCycleEngine(nx, ny, domain=domain, backend=backend, device=device, **engine_kw)
+        self.mode = {"double": "fp64", "fp64": "fp64", "single": "fp32", "fp32": "fp32", "refinement": "refine"}.get(
+            precision_strategy, "switch")
+        self.switch_threshold, self.tolerance, self.max_iterations = switch_threshold, tolerance, max_iterations
+        s0 = self.eng.part.slab(0)
+        self.s0 = s0
+        self.hxhy = s0.hx * s0.hy
+        self.ss = self.eng.be.scalar(2)
+        self.phase = None
+        self.precision_switches: List[Dict[str, Any]] = []
+
+    # -- right-hand side ---------------------------------------------------------------------------------------
+    def set_rhs_from_global(self, f_global) -> None:
+        """`f_global`: the full (nx, ny) float64 right-hand side (NumPy or tensor) present on every rank."""
+        b = self.eng.bufs(0, torch.float64)
+        s = self.s0
+        src = torch.as_tensor(f_global)[s.row0:s.row0 + s.loc_nx]
+        b.f.copy_(src)
+
+    def set_rhs_sinsin_device(self, amplitude: float = 2 * math.pi ** 2) -> None:
+        """Manufactured f = amplitude*sin(pi x) sin(pi y) generated in HBM on the slab (global coordinates)."""
+        from . import ops
+        b = self.eng.bufs(0, torch.float64)
+        s = self.s0
+        x0, x1, y0, y1 = self.eng.domain
+        xa = x0 + s.row0 * s.hx
+        xb = x0 + (s.row0 + s.loc_nx - 1) * s.hx
+        ops.fill_sinsin_(b.f, (xa, xb, y0, y1), amplitude, 1.0, 1.0)
+
+    def zero_boundary_ring_of_rhs(self) -> None:
+        b = self.eng.bufs(0, torch.float64)
+        s = self.s0
+        b.f[:, 0] = 0
+        b.f[:, -1] = 0
+        if s.own_lo == 0:
+            b.f[0, :] = 0
+        if s.own_hi == s.nx_glob:
+            b.f[-1, :] = 0
+
+    # -- solve loop ----------------------------------------------------------------------------------------------
+    def restart(self) -> float:
+        eng = self.eng
+        b64 = eng.bufs(0, torch.float64)
+        b64.u.zero_()
+        self.phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
+        self.history: List[float] = []
+        if self.phase == "refine":
+            return self._defect(with_update=False)
+        if self.phase == "fp32":
+            b32 = eng.bufs(0, torch.float32)
+            b32.f.copy_(b64.f)
+            b32.u.zero_()
+        return float("nan")
+
+    def _norm(self, slot: int) -> float:
+        self.eng.allreduce_sum(self.ss)
+        return float(np.sqrt(self.hxhy * self.ss[slot].item()))
+
+    def _defect(self, with_update: bool) -> float:
+        eng, s = self.eng, self.s0
+        b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
+        self.ss.zero_()
+        if with_update:
+            eng.be.vc_defect_pass(b64.u, b64.tmp, b64.f, s.hx, s.hy, e_in=b32.u, r_out=b32.f, sumsq_out=self.ss[1:2],
+                                  norm_rows=s.own_local)
+            b64.u, b64.tmp = b64.tmp, b64.u
+            eng.exchange(b64.u, 0)
+        else:
+            eng.be.vc_defect_pass(b64.u, None, b64.f, s.hx, s.hy, r_out=b32.f, sumsq_out=self.ss[1:2],
+                                  norm_rows=s.own_local)
+        eng.exchange(b32.f, 0)
+        return self._norm(1)
+
+    def step(self) -> float:
+        eng = self.eng
+        if self.phase == "refine":
+            eng.cycle(torch.float32, 0, u_zero=True)
+            norm = self._defect(with_update=True)
+        else:
+            dt = torch.float64 if self.phase == "fp64" else torch.float32
+            self.ss.zero_()
+            eng.cycle(dt, 0, u_zero=False, sumsq_out=self.ss[0:1])
+            norm = self._norm(0)
+        self.history.append(norm)
+        if self.phase == "refine" and self.mode == "switch" and self.tolerance <= norm <= self.switch_threshold:
+            self.precision_switches.append({"iteration": len(self.history), "residual": norm, "to": "float64"})
+            self.phase = "fp64"
+        return norm
+
+    def solve(self):
+        self.precision_switches = []
+        r0 = self.restart()
+        converged = False
+        for _ in range(self.max_iterations):
+            if self.step() < self.tolerance:
+                converged = True
+                break
+        dt = torch.float32 if self.mode == "fp32" else torch.float64
+        u = self.eng.bufs(0, dt).u
+        return u, {"converged": converged, "iterations": len(self.history), "residual_history": list(self.history),
+                   "final_residual": self.history[-1], "initial_residual": r0,
+                   "precision_switches": list(self.precision_switches), "dist_levels": self.eng.D,
+                   "num_levels": self.eng.num_levels, "halo_exchanges": self.eng.exchanges}
+
+
+# ======================================================================================================
+# bench.py leg for N > 1 GPUs (weak scaling: every GPU owns a (n-1) x n slab of a (N(n-1)+1) x n grid)
+# ======================================================================================================
+def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: str, ClockSampler):
+    import time
+
+    from . import _lib, ops
+    n = a.n
+    nx, ny = world * (n - 1) + 1, n
+    domain = (0.0, float(world), 0.0, 1.0)  # square cells, h = 1/(n-1): same spacing as the 1-GPU workload
+    tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
+    sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
+                                          tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
+                                          device=dev)
+    sol.set_rhs_sinsin_device()
+    sol.zero_boundary_ring_of_rhs()
+    sol.eng.exchange(sol.eng.bufs(0, torch.float64).f, 0)
+    state = {"solves": 0, "cycles": [], "last": None}
+
+    def step():
+        norm = sol.step()
+        if norm < tol or len(sol.history) >= 30:
+            state["solves"] += 1
+            state["cycles"].append(len(sol.history))
+            state["last"] = list(sol.history)
+            sol.restart()
+
+    sol.restart()
+    for _ in range(max(3, a.warmup)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = _lib.call("mg_launch_count")
+    ops.TIMER = ops.KernelTimer(min_points=(n - 1) * n // 2) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ex0 = sol.eng.exchanges
+    with ClockSampler(dev.index) as clk:
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(a.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+    ms_local = e0.elapsed_time(e1)
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    launches = _lib.call("mg_launch_count") - launches0
+    kern = ops.TIMER.summary() if ops.TIMER is not None else {}
+    ops.TIMER = None
+    value = nx * ny * a.steps / (ms * 1e-3)
+
+    kernels = {}
+    roof = None
+    s0 = sol.s0
+    pts = s0.loc_nx * ny
+    for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
+        name, dtn, _ = tag.split("/")
+        w = 8 if dtn == "f64" else 4
+        if "resid32" in name or name.startswith("update"):
+            b = (20 if "resid32" in name else 0) + (12 if name.startswith("update") else 0)
+        else:
+            b = 3.0 * w - (w if name.startswith("Z+") else 0) + (0.25 * w if "P+" in name else 0) + (0.25 * w if "+R" in name else 0)
+        ach = b * pts / (d["mean_ms"] * 1e-3) / 1e9
+        kernels[tag] = {"launches": d["launches"], "mean_ms": round(d["mean_ms"], 4), "hbm_gbs": round(ach, 1),
+                        "frac_of_peak": round(ach / peak, 4), "share_of_step": round(d["total_ms"] / ms, 4)}
+        if roof is None:
+            roof = {"bound": "hbm", "kernel": tag, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": b * pts, "rank": 0}
+
+    # end to end: pinned host slab of f -> device, solve, device slab of u -> pinned host (every rank its slab)
+    e2e = None
+    if not a.no_e2e:
+        b64 = sol.eng.bufs(0, torch.float64)
+        f_host = torch.empty((s0.loc_nx, ny), dtype=torch.float64, pin_memory=True)
+        u_host = torch.empty((s0.loc_nx, ny), dtype=torch.float64, pin_memory=True)
+        f_host.copy_(b64.f)
+        torch.cuda.synchronize()
+        tot_t, tot_c, reps = 0.0, 0, 2
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            b64.f.copy_(f_host, non_blocking=True)
+            u, info = sol.solve()
+            u_host.copy_(u, non_blocking=True)
+            torch.cuda.synchronize()
+            dist.barrier()
+            tot_t += time.perf_counter() - t0
+            tot_c += info["iterations"]
+        tt = torch.tensor([tot_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": nx * ny * tot_c / float(tt.item()), "unit": "unknowns/s",
+               "h2d_bytes_per_step": s0.loc_nx * ny * 8 * world, "d2h_bytes_per_step": s0.loc_nx * ny * 8 * world,
+               "step": "one distributed solve(): every rank uploads its pinned host slab of f and downloads its slab of u",
+               "seconds_per_solve": float(tt.item()) / reps, "iterations": info["iterations"],
+               "final_residual": info["final_residual"]}
+    clocks = clk.summary()
+    return {
+        "metric": _metric_name(), "value": value, "unit": "unknowns/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 cycle / f64 iterate+residual" if sol.mode in ("switch", "refine") else sol.mode,
+        "data": "synthetic",
+        "config": {"workload": f"2D Poisson {nx}x{ny} ({n - 1} rows per GPU) manufactured sin*sin on (0,{world})x(0,1), "
+                               f"{a.cycle}(2,2) red-black GS, precision_strategy={a.strategy}, row slabs over {world} GPUs",
+                   "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": GHOST,
+                   "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
+                   "halo_exchanges_per_step": (sol.eng.exchanges - ex0) / max(1, a.steps), "cuda_graphs": False,
+                   "l2": "slab arrays (>= 1 GB) exceed the 126 MB L2; no flush needed",
+                   "cycles_per_solve": state["cycles"][-3:], "last_residual_history": state["last"]},
+        "roofline": roof, "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+
+
+def _metric_name() -> str:
+    import json
+    import os
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        return json.load(open(os.path.join(root, "BASELINE.json")))["metric"]
+    except Exception:
+        return "V-cycle fine-grid unknowns/sec + smoother HBM GB/s vs peak at 1/2/4/8 B200"

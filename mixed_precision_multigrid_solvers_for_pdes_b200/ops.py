@@ -233,7 +233,7 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
             sweeps: int = 2, omega: float = 1.0, coefficient: float = -1.0,
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
             sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
-            u_zero: bool = False) -> None:
+            u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None) -> None:
     """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS sweeps -> [coarse_out = R(f - A u)] or
     [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored).
     ``u_zero``: treat u_in as identically zero without reading it."""
@@ -255,14 +255,15 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.call("mg_vc_pass", None if u_zero else u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None,
+    nlo, nhi = norm_rows if norm_rows is not None else (0, -1)
+    _lib.call("mg_vc_pass_slab", None if u_zero else u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None,
               f.data_ptr(),
               coarse_in.data_ptr() if coarse_in is not None else None,
               coarse_out.data_ptr() if coarse_out is not None else None,
               sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
               nx, ny, 0 if u_zero else ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
               ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
-              hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, stream_ptr())
+              hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, nlo, nhi, stream_ptr())
     if timed:
         ev1.record()
         tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"rbgs{sweeps}"
@@ -282,7 +283,7 @@ def _loader_flag(loader: str) -> int:
 def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
                    e_in: Optional[torch.Tensor] = None, r_out: Optional[torch.Tensor] = None,
                    sumsq_out: Optional[torch.Tensor] = None, coefficient: float = -1.0, loader: str = "tma",
-                   rows: int = 0) -> None:
+                   rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None) -> None:
     """Mixed-precision defect-correction pass on the fp64 iterate (one HBM pass):
     u_out = u_in + e_in (fp32 correction; None: u unchanged, nothing stored), r_out = fp32(f - A u_out),
     sumsq_out[0] = sum of the squared fp64 residual."""
@@ -298,11 +299,12 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.call("mg_vc_defect_pass", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+    nlo, nhi = norm_rows if norm_rows is not None else (0, -1)
+    _lib.call("mg_vc_defect_pass_slab", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
               e_in.data_ptr() if e_in is not None else None, r_out.data_ptr() if r_out is not None else None,
               sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
               nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(e_in) if e_in is not None else 0,
-              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, stream_ptr())
+              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, stream_ptr())
     if timed:
         ev1.record()
         TIMER.records.append((("update+" if e_in is not None else "") + ("resid32+N" if r_out is not None else "")

@@ -1,0 +1,87 @@
+"""CPU stand-in for the fused slab kernels, used ONLY by the gloo tests of the distributed host logic
+(partitioning, ghost exchange, agglomeration, norm all-reduce).  It reproduces the SEMANTICS of
+mg_vc_pass_slab / mg_vc_defect_pass_slab on dense CPU tensors with the NumPy oracle: the local array is a
+stand-alone grid whose first/last rows are never updated, an even row count is allowed for the transfers,
+only `norm_rows` enter the residual sum."""
+import numpy as np
+import torch
+
+from oracle import np_oracle as O
+
+
+def _np(t):
+    return t.numpy()
+
+
+class _CoarseEmu:
+    def __init__(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max):
+        self.args = dict(max_levels=levels, cycle_type=cycle_type, pre=pre, post=post, coarse_tolerance=coarse_tol,
+                         coarse_max_iterations=coarse_max, domain=domain)
+        self.nx, self.ny = nx, ny
+        self._b = {}
+
+    def bufs(self, dtype):
+        if dtype not in self._b:
+            class B:
+                pass
+            b = B()
+            b.f = torch.zeros(self.nx, self.ny, dtype=dtype)
+            b.u = torch.zeros(self.nx, self.ny, dtype=dtype)
+            self._b[dtype] = b
+        return self._b[dtype]
+
+    def cycle(self, dtype, u_zero):
+        b = self.bufs(dtype)
+        npdt = np.float64 if dtype == torch.float64 else np.float32
+        s = O.OracleMultigrid(self.nx, self.ny, dtype=npdt, **self.args)
+        L = len(s.grids)
+        s.level_dtypes = [npdt] * (L - 1) + [np.float64]
+        s.rhs[0] = _np(b.f).copy()
+        u0 = np.zeros_like(_np(b.u)) if u_zero else _np(b.u).copy()
+        u = s._cycle(u0, 0)
+        b.u.copy_(torch.from_numpy(np.ascontiguousarray(u)).to(dtype))
+        return b.u
+
+
+class OracleBackend:
+    def empty(self, nx, ny, dtype):
+        return torch.zeros(nx, ny, dtype=dtype)
+
+    def scalar(self, n=1):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def make_coarse_engine(self, *a):
+        return _CoarseEmu(*a)
+
+    def vc_pass(self, u_in, u_out, f, hx, hy, *, sweeps=2, omega=1.0, coefficient=-1.0, coarse_in=None,
+                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0):
+        F = _np(f)
+        nx = F.shape[0]
+        nxo = nx if nx % 2 == 1 else nx - 1
+        U = np.zeros_like(F) if u_zero else _np(u_in).copy()
+        if coarse_in is not None:
+            C = _np(coarse_in)[:(nxo - 1) // 2 + 1]
+            U[:nxo] += O.prolong(C)
+        U = O.rbgs_smooth(U, F, hx, hy, omega, sweeps)
+        if u_out is not None:
+            u_out.copy_(torch.from_numpy(U))
+        if coarse_out is not None or sumsq_out is not None:
+            R = O.residual(U, F, hx, hy, coefficient)
+            if coarse_out is not None:
+                rc = O.restrict(R[:nxo])
+                coarse_out[:rc.shape[0]].copy_(torch.from_numpy(rc))
+            if sumsq_out is not None:
+                lo, hi = norm_rows if norm_rows is not None else (0, nx)
+                sumsq_out[0] = float(np.sum(R[lo:hi].astype(np.float64) ** 2))
+
+    def vc_defect_pass(self, u_in, u_out, f, hx, hy, *, e_in=None, r_out=None, sumsq_out=None, coefficient=-1.0,
+                       norm_rows=None, rows=0):
+        U = _np(u_in).copy()
+        if e_in is not None:
+            U = U + _np(e_in).astype(np.float64)
+            u_out.copy_(torch.from_numpy(U))
+        if r_out is not None:
+            R = O.residual(U, _np(f), hx, hy, coefficient)
+            r_out.copy_(torch.from_numpy(R.astype(np.float32)))
+            lo, hi = norm_rows if norm_rows is not None else (0, U.shape[0])
+            sumsq_out[0] = float(np.sum(R[lo:hi] ** 2))

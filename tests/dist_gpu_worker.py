@@ -1,0 +1,41 @@
+"""torchrun worker of tests/test_gpu_distributed.py: solve a 1025 x 513 problem on WORLD_SIZE GPUs, rank 0 saves."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedMixedPrecisionSolver  # noqa: E402
+from oracle import np_oracle as O  # noqa: E402
+
+
+def main():
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    nx, ny, dom = 1025, 513, (0.0, 2.0, 0.0, 1.0)
+    g = O.OGrid(nx, ny, dom)
+    x, y = g.coords()
+    f = 2 * np.pi ** 2 * np.sin(np.pi * x)[:, None] * np.sin(np.pi * y)[None, :]
+    res = {}
+    for strategy in ("double", "adaptive"):
+        sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy, tolerance=1e-8,
+                                              agglomerate_below=129, device=dev)
+        sol.set_rhs_from_global(torch.from_numpy(f).to(dev))
+        u, info = sol.solve()
+        full = sol.eng.gather_solution(u)
+        res[strategy] = {"iterations": info["iterations"], "history": info["residual_history"],
+                         "u": full.cpu().numpy()}
+        res["exchanges"] = info["halo_exchanges"]
+        res["D"] = sol.eng.D
+    if dist.get_rank() == 0:
+        torch.save(res, sys.argv[1])
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
