@@ -222,6 +222,23 @@ class DistributedCycleEngine:
                                                  coarse_tolerance, coarse_max_iterations)
         self.exchanges = 0
 
+    # -- buffer roles (for CUDA-graph replay) ---------------------------------------------------------------
+    def _all_bufs(self):
+        inner = getattr(self.coarse, "eng", None)
+        mine = list(self._bufs.values())
+        return mine + ([b for lv in inner.levels for b in lv._bufs.values()] if inner is not None else [])
+
+    def buffer_state(self):
+        return tuple(b.u.data_ptr() for b in self._all_bufs())
+
+    def snapshot_roles(self):
+        return [(b, b.u, b.tmp) for b in self._all_bufs()]
+
+    @staticmethod
+    def restore_roles(snap) -> None:
+        for b, u, tmp in snap:
+            b.u, b.tmp = u, tmp
+
     # -- buffers ------------------------------------------------------------------------------------------
     def bufs(self, l: int, dtype) -> _Bufs:
         key = (l, dtype)
@@ -371,7 +388,7 @@ class DistributedMixedPrecisionSolver:
 
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), precision_strategy: str = "adaptive",
                  switch_threshold: float = 1e-6, tolerance: float = 1e-8, max_iterations: int = 50, backend=None,
-                 device=None, **engine_kw):
+                 device=None, use_cuda_graphs: bool = False, **engine_kw):
         self.eng = DistributedCycleEngine(nx, ny, domain=domain, backend=backend, device=device, **engine_kw)
         self.mode = {"double": "fp64", "fp64": "fp64", "single": "fp32", "fp32": "fp32", "refinement": "refine"}.get(
             precision_strategy, "switch")
@@ -382,6 +399,13 @@ class DistributedMixedPrecisionSolver:
         self.ss = self.eng.be.scalar(2)
         self.phase = None
         self.precision_switches: List[Dict[str, Any]] = []
+        for l in range(self.eng.D + 1):  # final shape of the buffer-role state before the first step
+            for dt in ((torch.float64, torch.float32) if self.mode in ("switch", "refine") else
+                       ((torch.float64,) if self.mode == "fp64" else (torch.float32,))):
+                self.eng.bufs(l, dt)
+        from .solvers.graphs import GraphCache
+        self.graphs = GraphCache(self.eng.buffer_state, self.eng.snapshot_roles, self.eng.restore_roles,
+                                 enabled=use_cuda_graphs)
 
     # -- right-hand side ---------------------------------------------------------------------------------------
     def set_rhs_from_global(self, f_global) -> None:
@@ -427,10 +451,13 @@ class DistributedMixedPrecisionSolver:
         return float("nan")
 
     def _norm(self, slot: int) -> float:
-        self.eng.allreduce_sum(self.ss)
         return float(np.sqrt(self.hxhy * self.ss[slot].item()))
 
     def _defect(self, with_update: bool) -> float:
+        self.graphs.run("defect_u" if with_update else "defect", lambda: self._launch_defect(with_update))
+        return self._norm(1)
+
+    def _launch_defect(self, with_update: bool) -> None:
         eng, s = self.eng, self.s0
         b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
         self.ss.zero_()
@@ -443,17 +470,24 @@ class DistributedMixedPrecisionSolver:
             eng.be.vc_defect_pass(b64.u, None, b64.f, s.hx, s.hy, r_out=b32.f, sumsq_out=self.ss[1:2],
                                   norm_rows=s.own_local)
         eng.exchange(b32.f, 0)
-        return self._norm(1)
+        eng.allreduce_sum(self.ss)
+
+    def _launch_refine(self) -> None:
+        self.eng.cycle(torch.float32, 0, u_zero=True)
+        self._launch_defect(True)
+
+    def _launch_uniform(self, dt) -> None:
+        self.ss.zero_()
+        self.eng.cycle(dt, 0, u_zero=False, sumsq_out=self.ss[0:1])
+        self.eng.allreduce_sum(self.ss)
 
     def step(self) -> float:
-        eng = self.eng
         if self.phase == "refine":
-            eng.cycle(torch.float32, 0, u_zero=True)
-            norm = self._defect(with_update=True)
+            self.graphs.run("refine", self._launch_refine)
+            norm = self._norm(1)
         else:
             dt = torch.float64 if self.phase == "fp64" else torch.float32
-            self.ss.zero_()
-            eng.cycle(dt, 0, u_zero=False, sumsq_out=self.ss[0:1])
+            self.graphs.run(self.phase, lambda: self._launch_uniform(dt))
             norm = self._norm(0)
         self.history.append(norm)
         if self.phase == "refine" and self.mode == "switch" and self.tolerance <= norm <= self.switch_threshold:
@@ -490,7 +524,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
-                                          device=dev)
+                                          device=dev, use_cuda_graphs=not a.no_graphs)
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
     sol.eng.exchange(sol.eng.bufs(0, torch.float64).f, 0)
@@ -505,12 +539,12 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
             sol.restart()
 
     sol.restart()
+    from .solvers.graphs import prime
+    primed = prime(step, sol.graphs, lambda: state["solves"])  # setup: capture every step graph (see bench.py)
     for _ in range(max(3, a.warmup)):
         step()
     torch.cuda.synchronize()
     dist.barrier()
-    launches0 = _lib.call("mg_launch_count")
-    ops.TIMER = ops.KernelTimer(min_points=(n - 1) * n // 2) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ex0 = sol.eng.exchanges
     with ClockSampler(dev.index) as clk:
@@ -523,13 +557,25 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
         torch.cuda.synchronize()
         dist.barrier()
     ms_local = e0.elapsed_time(e1)
+    ex_per_step = (sol.eng.exchanges - ex0) / max(1, a.steps)
     t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    value = nx * ny * a.steps / (ms * 1e-3)
+    # per-kernel durations and launch counts: the same steps once more, eagerly, with events on rank 0
+    sol.graphs.enabled = False
+    ops.TIMER = ops.KernelTimer(min_points=(n - 1) * n // 2) if rank == 0 else None
+    launches0 = _lib.call("mg_launch_count")
+    ex0 = sol.eng.exchanges
+    for _ in range(a.steps):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
     launches = _lib.call("mg_launch_count") - launches0
+    ex_per_step = (sol.eng.exchanges - ex0) / max(1, a.steps)
     kern = ops.TIMER.summary() if ops.TIMER is not None else {}
     ops.TIMER = None
-    value = nx * ny * a.steps / (ms * 1e-3)
+    sol.graphs.enabled = not a.no_graphs
 
     kernels = {}
     roof = None
@@ -544,7 +590,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
             b = 3.0 * w - (w if name.startswith("Z+") else 0) + (0.25 * w if "P+" in name else 0) + (0.25 * w if "+R" in name else 0)
         ach = b * pts / (d["mean_ms"] * 1e-3) / 1e9
         kernels[tag] = {"launches": d["launches"], "mean_ms": round(d["mean_ms"], 4), "hbm_gbs": round(ach, 1),
-                        "frac_of_peak": round(ach / peak, 4), "share_of_step": round(d["total_ms"] / ms, 4)}
+                        "frac_of_peak": round(ach / peak, 4)}
         if roof is None:
             roof = {"bound": "hbm", "kernel": tag, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
@@ -587,7 +633,8 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                                f"{a.cycle}(2,2) red-black GS, precision_strategy={a.strategy}, row slabs over {world} GPUs",
                    "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": GHOST,
                    "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
-                   "halo_exchanges_per_step": (sol.eng.exchanges - ex0) / max(1, a.steps), "cuda_graphs": False,
+                   "halo_exchanges_per_step": ex_per_step, "cuda_graphs": (not a.no_graphs),
+                   "graphs_captured": sol.graphs.captured, "priming_solves": primed,
                    "l2": "slab arrays (>= 1 GB) exceed the 126 MB L2; no flush needed",
                    "cycles_per_solve": state["cycles"][-3:], "last_residual_history": state["last"]},
         "roofline": roof, "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),

@@ -37,6 +37,7 @@ from ..device import empty_field, like_input, require_cuda, to_device
 from ..operators.laplacian import LaplacianOperator
 from ..operators.transfer import ProlongationOperator, RestrictionOperator
 from .engine import CycleEngine
+from .graphs import GraphCache
 from .smoothers import GaussSeidelSmoother, JacobiSmoother
 
 _STRATEGIES = {
@@ -85,7 +86,7 @@ class MixedPrecisionMultigrid:
         # One multigrid cycle is ~3 launches per level, most of them microseconds long on the coarse levels:
         # each (phase, buffer-role state) is captured once into a CUDA graph and replayed afterwards.
         self.use_cuda_graphs = use_cuda_graphs
-        self._graphs: Dict[Any, Any] = {}
+        self._graph_cache = None
         self.enable_precision_monitoring = False
         self.precision_switches: List[Dict[str, Any]] = []
         self._engine: Optional[CycleEngine] = None
@@ -136,35 +137,26 @@ class MixedPrecisionMultigrid:
         self._shape, self._domain, self._grid = (nx, ny), tuple(domain), g
         self._sumsq = torch.zeros(2, dtype=torch.float64, device=dev)
         self._pinned_out = None
-        self._graphs = {}
+        eng = self._engine
+        # allocate every (level, dtype) buffer the chosen strategy touches now, so the buffer-role state that keys
+        # the CUDA graphs has its final shape before the first step
+        L = eng.num_levels
+        plans = {"fp64": [[torch.float64] * L], "fp32": [[torch.float32] * L]}.get(
+            self.mode, [[torch.float64] * L, [torch.float32] * (L - 1) + [torch.float64]])
+        for plan in plans:
+            for lv, dt in zip(eng.levels, plan):
+                lv.bufs(dt)
+        self._graph_cache = GraphCache(eng.buffer_state, eng.snapshot_roles, eng.restore_roles, self.use_cuda_graphs)
         # fp64 iterate / rhs of the refinement phase live in the engine's fp64 level-0 buffers
 
-    # -- CUDA-graph replay of one step -----------------------------------------------------------------------
+    # -- CUDA-graph replay of one step (solvers/graphs.py) ------------------------------------------------------
     def _graphed(self, name: str, launch) -> None:
-        """Run `launch()` (a fixed sequence of kernel launches writing its norm into self._sumsq[2]) through a
-        CUDA graph captured per (step kind, buffer-role state).  The first use of a state runs eagerly (it
-        also warms every lazily allocated workspace), the second captures, later ones replay."""
-        eng = self._engine
-        if not self.use_cuda_graphs:
-            launch()
-            return
-        key = (name, eng.buffer_state())
-        entry = self._graphs.get(key)
-        if entry is None:  # first visit: eager
-            launch()
-            self._graphs[key] = "warm"
-            return
-        if entry == "warm":  # second visit: capture (capture does not execute), then fall through to replay
-            before = eng.snapshot_roles()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                launch()
-            after = eng.snapshot_roles()
-            eng.restore_roles(before)
-            entry = self._graphs[key] = (g, after)
-        g, after = entry
-        g.replay()
-        eng.restore_roles(after)
+        self._graph_cache.enabled = self.use_cuda_graphs
+        self._graph_cache.run(name, launch)
+
+    @property
+    def _graphs(self):
+        return self._graph_cache.entries
 
     def _norm_from(self, ss: torch.Tensor) -> float:
         return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))

@@ -22,11 +22,16 @@ def main():
     x, y = g.coords()
     f = 2 * np.pi ** 2 * np.sin(np.pi * x)[:, None] * np.sin(np.pi * y)[None, :]
     res = {}
-    for strategy in ("double", "adaptive"):
-        sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy, tolerance=1e-8,
-                                              agglomerate_below=129, device=dev)
+    for strategy in ("double", "adaptive", "adaptive_graphs"):
+        sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy.split("_")[0],
+                                              tolerance=1e-8, agglomerate_below=129, device=dev,
+                                              use_cuda_graphs=strategy.endswith("graphs"))
         sol.set_rhs_from_global(torch.from_numpy(f).to(dev))
         u, info = sol.solve()
+        if strategy.endswith("graphs"):  # second and third solve replay captured graphs (NCCL send/recv included)
+            u, info = sol.solve()
+            u, info = sol.solve()
+            res["graphs_captured"] = sol.graphs.captured
         full = sol.eng.gather_solution(u)
         res[strategy] = {"iterations": info["iterations"], "history": info["residual_history"],
                          "u": full.cpu().numpy()}

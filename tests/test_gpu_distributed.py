@@ -45,6 +45,10 @@ def test_two_gpus_equal_one_gpu(tmp_path):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     r1 = torch.load(out + "1", weights_only=False)
     r2 = torch.load(out + "2", weights_only=False)
+    assert r2["graphs_captured"] > 0
+    for r in (r1, r2):  # CUDA-graph replay (incl. the NCCL exchanges) == eager, bit for bit
+        assert np.array_equal(r["adaptive"]["u"], r["adaptive_graphs"]["u"])
+        assert r["adaptive"]["history"] == r["adaptive_graphs"]["history"]
     for key in ("double", "adaptive"):
         assert r1[key]["iterations"] == r2[key]["iterations"]
         np.testing.assert_allclose(r2[key]["history"], r1[key]["history"], rtol=1e-10)
