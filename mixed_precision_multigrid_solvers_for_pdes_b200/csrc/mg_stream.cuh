@@ -156,10 +156,35 @@ __device__ __forceinline__ T residual_fast(const StencilScalars<T>& s, T uc, T u
   return fma(-s.coeff, t, f);
 }
 
+// Isotropic (hx == hy), unrelaxed (omega == 1) specialisation: 5 instead of 8 instructions per point.
+// ((a+b)+(c+d))*ih2 equals (a+b)*ih2 + (c+d)*ih2 bit for bit when ih2 is a power of two (scaling by a power
+// of two commutes with rounding), and omega = 1 makes the relaxation blend the identity.
+template <typename T>
+__device__ __forceinline__ T relax_iso1(const StencilScalars<T>& s, T up, T dn, T rt, T lf, T rhs) {
+  const T sum = (up + dn) + (rt + lf);
+  return fma(sum, s.ihx2, rhs) * s.inv_neg_diag;
+}
+template <typename T>
+__device__ __forceinline__ T residual_iso(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
+  const T sum = (up + dn) + (rt + lf);
+  const T t = fma((T)-4, uc, sum);  // h^2 * lap_h u
+  return fma(-s.coeff * s.ihx2, t, f);
+}
+template <bool SIMPLE, typename T>
+__device__ __forceinline__ T relax_sel(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
+  if (SIMPLE) return relax_iso1<T>(s, up, dn, rt, lf, rhs);
+  return relax_fast<T>(s, uc, up, dn, rt, lf, rhs);
+}
+template <bool SIMPLE, typename T>
+__device__ __forceinline__ T residual_sel(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
+  if (SIMPLE) return residual_iso<T>(s, uc, up, dn, rt, lf, f);
+  return residual_fast<T>(s, uc, up, dn, rt, lf, f);
+}
+
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NU, int FRONT, int BACK, int LOADER, int WARPS, int NSTAGE, int RB>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int WARPS, int NSTAGE, int RB>
 __global__ void __launch_bounds__(WARPS * 32)
     rbgs_stream_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_f,
                        const __grid_constant__ CUtensorMap map_e, const PassParams p, const StencilScalars<T> sc) {
@@ -328,6 +353,9 @@ __global__ void __launch_bounds__(WARPS * 32)
   //      touches is an interior point, so there are no boundary tests, selects or divergent branches. ----
   auto process_box = [&](auto masked_tag, const int ib, const T* su, const T* sf, const float* se) {
     constexpr bool MASKED = decltype(masked_tag)::value;
+    // rows stored by this box: ib - 2NU ... ib + RB - 1 - 2NU; all owned by the tile?  (uniform)
+    const bool rows_owned = (ib - 2 * NU >= I0) && (ib + RB - 1 - 2 * NU < I1);
+    T* orow = uout + (int64_t)(ib - 2 * NU) * p.ld_out + jbase;  // running output row pointer
 #pragma unroll
     for (int k = 0; k < RB; ++k) {
       const int i = ib + k;  // newest row; parity of i == parity of k
@@ -393,30 +421,33 @@ __global__ void __launch_bounds__(WARPS * 32)
           const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element, compile-time after unrolling
           if (e0 == 0) {
             const T lfx = shfl_up1(w[s][3]);
-            const T n0 = relax_fast<T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
-            const T n2 = relax_fast<T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
+            const T n0 = relax_sel<SIMPLE, T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
+            const T n2 = relax_sel<SIMPLE, T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
             w[s][0] = (!MASKED || (upd & 1u)) ? n0 : w[s][0];
             w[s][2] = (!MASKED || (upd & 4u)) ? n2 : w[s][2];
           } else {
             const T rtx = shfl_dn1(w[s][0]);
-            const T n1 = relax_fast<T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
-            const T n3 = relax_fast<T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
+            const T n1 = relax_sel<SIMPLE, T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
+            const T n3 = relax_sel<SIMPLE, T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
             w[s][1] = (!MASKED || (upd & 2u)) ? n1 : w[s][1];
             w[s][3] = (!MASKED || (upd & 8u)) ? n3 : w[s][3];
           }
         }
       }
 
-      // (3) the row of age 2NU is final: store the owned part
+      // (3) the row of age 2NU is final: store the owned part (predicated stores, no divergent branch)
       {
         const int qf = i - 2 * NU;
-        if (store_u && qf >= I0 && qf < I1 && own != 0u) {
-          T* dst = uout + (int64_t)qf * p.ld_out + jbase;
+        const bool row_ok = store_u && (rows_owned || (qf >= I0 && qf < I1));
+        T* dst = orow;
+        orow += p.ld_out;
+        if (!MASKED) {  // interior strip: ownership changes only at even columns
+          if (row_ok && own == 0xFu) stg4(dst, w[2 * NU]);
+          if (row_ok && own == 0x3u) stg2(dst, w[2 * NU][0], w[2 * NU][1]);
+          if (row_ok && own == 0xCu) stg2(dst + 2, w[2 * NU][2], w[2 * NU][3]);
+        } else if (row_ok && own != 0u) {
           if (own == 0xFu) {
             stg4(dst, w[2 * NU]);
-          } else if (!MASKED) {  // interior strip: ownership changes only at even columns
-            if ((own & 3u) == 3u) stg2(dst, w[2 * NU][0], w[2 * NU][1]);
-            if ((own & 12u) == 12u) stg2(dst + 2, w[2 * NU][2], w[2 * NU][3]);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -434,10 +465,10 @@ __global__ void __launch_bounds__(WARPS * 32)
           if (!MASKED || (q2 >= 1 && q2 <= nx - 2)) {
             const T lfx = shfl_up1(w[A][3]);
             const T rtx = shfl_dn1(w[A][0]);
-            const T r0 = residual_fast<T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
-            const T r1 = residual_fast<T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
-            const T r2 = residual_fast<T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
-            const T r3 = residual_fast<T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
+            const T r0 = residual_sel<SIMPLE, T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
+            const T r1 = residual_sel<SIMPLE, T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
+            const T r2 = residual_sel<SIMPLE, T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
+            const T r3 = residual_sel<SIMPLE, T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
             r[0] = (!MASKED || (upd & 1u)) ? r0 : fr[A][0];
             r[1] = (!MASKED || (upd & 2u)) ? r1 : fr[A][1];
             r[2] = (!MASKED || (upd & 4u)) ? r2 : fr[A][2];
@@ -450,11 +481,16 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (HAS_NORM) {
           if (q2 >= I0 && q2 < I1) {
             if (q2 >= p.norm_row_lo && q2 < p.norm_row_hi) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const T sq = r[e] * r[e];  // squared in T like NumPy's field**2, accumulated in fp64
-                acc += ((own >> e) & 1u) ? (double)sq : 0.0;
+              // squares formed in T (like NumPy's field**2), the row's four summed in T, one fp64 add per row
+              T rowsum;
+              if (!MASKED && own == 0xFu) {
+                rowsum = (r[0] * r[0] + r[1] * r[1]) + (r[2] * r[2] + r[3] * r[3]);
+              } else {
+                const T m0 = (own & 1u) ? r[0] : (T)0, m1 = (own & 2u) ? r[1] : (T)0;
+                const T m2 = (own & 4u) ? r[2] : (T)0, m3 = (own & 8u) ? r[3] : (T)0;
+                rowsum = (m0 * m0 + m1 * m1) + (m2 * m2 + m3 * m3);
               }
+              acc += (double)rowsum;
             }
             if (BACK == BACK_RESID && own != 0u) {
               float* dst = p.resid_out + (int64_t)q2 * p.ld_ro + jbase;

@@ -5,10 +5,10 @@
 
 namespace mg {
 namespace stream {
-int launch_pass_f32_tma(int, int, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f32_cpa(int, int, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f64_tma(int, int, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
-int launch_pass_f64_cpa(int, int, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f32_tma(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f32_cpa(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_tma(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f64_cpa(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -50,12 +50,21 @@ static inline int num_strips(int ny, int nu, int back) {
   while ((int64_t)stride * k - 4 + hi < ny - 1) ++k;
   return k + 1;
 }
-static inline int pick_rows(int nx, int nstrips, int override_rows) {
+// Rows per tile.  A warp streams R + lead + tail rows sequentially, so a launch lasts about
+// waves * (R + overlap) row-steps, with waves = warps needed / warps resident.  Large grids want tall tiles
+// (overlap amortised), small grids want short ones (short critical path, all SMs busy).
+static inline int pick_rows(int nx, int nstrips, int overlap, int override_rows) {
   if (override_rows > 0) return (override_rows + 1) & ~1;
-  const int target = sm_count() * 12;  // warps we would like in flight
-  int r = 512;
-  while (r > 32 && (int64_t)nstrips * ((nx + r - 1) / r) < target) r >>= 1;
-  return r;
+  const int64_t capacity = (int64_t)sm_count() * 12;  // resident warps (3 blocks of 4 warps per SM)
+  int best = 512;
+  int64_t best_cost = INT64_MAX;
+  for (int r = 512; r >= 8; r >>= 1) {
+    const int64_t warps = (int64_t)nstrips * ((nx + r - 1) / r);
+    const int64_t waves = (warps + capacity - 1) / capacity;
+    const int64_t cost = waves * (r + overlap);
+    if (cost < best_cost) { best_cost = cost; best = r; }
+  }
+  return best;
 }
 
 }  // namespace stream
@@ -117,7 +126,7 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   p.norm_row_lo = norm_lo < 0 ? 0 : norm_lo;
   p.norm_row_hi = (norm_hi < 0 || norm_hi > nx) ? nx : norm_hi;
   p.nstrips = num_strips(ny, sweeps, back);
-  p.rows_per_tile = pick_rows(nx, p.nstrips, rows_override);
+  p.rows_per_tile = pick_rows(nx, p.nstrips, 4 * sweeps + (back ? 4 : 0) + 2, rows_override);
   p.store_u = store ? 1 : 0;
 
   Maps m;
@@ -130,13 +139,16 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
     if (rc != MG_OK) return rc;
   }
   cudaStream_t st = as_stream(stream);
+  const bool simple = (omega == 1.0) && (hx == hy);  // isotropic, unrelaxed: the 5-instruction point update
   int rc;
   if (dtype == MG_F64) {
     auto sc = make_scalars<double>(hx, hy, omega, coefficient);
-    rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, m, p, sc, st) : launch_pass_f64_tma(sweeps, front, back, m, p, sc, st);
+    rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, simple, m, p, sc, st)
+             : launch_pass_f64_tma(sweeps, front, back, simple, m, p, sc, st);
   } else {
     auto sc = make_scalars<float>(hx, hy, omega, coefficient);
-    rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, m, p, sc, st) : launch_pass_f32_tma(sweeps, front, back, m, p, sc, st);
+    rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, simple, m, p, sc, st)
+             : launch_pass_f32_tma(sweeps, front, back, simple, m, p, sc, st);
   }
   if (rc != MG_OK) return rc;
   if (norm) {
@@ -152,7 +164,7 @@ extern "C" {
 int mg_vc_workspace_doubles(int nx, int ny) {
   if (nx < 3 || ny < 3) return 0;
   const int nstrips = num_strips(ny, 0, 1) + WARPS;  // smallest stride => most strips
-  const int ntiles = (nx + 31) / 32;
+  const int ntiles = (nx + 7) / 8;
   return nstrips * ntiles + 8;
 }
 

@@ -17,10 +17,10 @@ struct Maps {
   CUtensorMap u, f, e;
 };
 
-template <typename T, int NU, int FRONT, int BACK, int LOADER>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE>
 static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
   constexpr int NS = Stages<T>::N;
-  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, WARPS, NS, RB>;
+  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, WARPS, NS, RB>;
   constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0);
   constexpr size_t smem = (size_t)WARPS * NS * stage_bytes;
   static bool configured[64] = {false};
@@ -37,10 +37,12 @@ static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T
 }
 
 template <typename T, int LOADER>
-int launch_pass(int nu, int front, int back, const Maps& m, const PassParams& p, const StencilScalars<T>& sc,
-                cudaStream_t st) {
-#define MG_CASE(NU_, FR_, BK_) \
-  if (nu == NU_ && front == FR_ && back == BK_) return launch_one<T, NU_, FR_, BK_, LOADER>(m, p, sc, st);
+int launch_pass(int nu, int front, int back, bool simple, const Maps& m, const PassParams& p,
+                const StencilScalars<T>& sc, cudaStream_t st) {
+#define MG_CASE(NU_, FR_, BK_)                                                           \
+  if (nu == NU_ && front == FR_ && back == BK_)                                          \
+    return simple ? launch_one<T, NU_, FR_, BK_, LOADER, true>(m, p, sc, st)             \
+                  : launch_one<T, NU_, FR_, BK_, LOADER, false>(m, p, sc, st);
   MG_CASE(0, FRONT_NONE, BACK_RESTRICT) MG_CASE(0, FRONT_NONE, BACK_NORM)
   MG_CASE(0, FRONT_PROLONG, BACK_NONE) MG_CASE(0, FRONT_PROLONG, BACK_RESTRICT) MG_CASE(0, FRONT_PROLONG, BACK_NORM)
   MG_CASE(1, FRONT_NONE, BACK_NONE) MG_CASE(1, FRONT_NONE, BACK_RESTRICT) MG_CASE(1, FRONT_NONE, BACK_NORM)

@@ -73,6 +73,12 @@ def main():
                         fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, **kw)), 3.25 * w, 2
                     elif mode == "up2norm":
                         fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, sumsq_out=ss, **kw)), 3.25 * w, 2
+                    elif mode == "zdown2":
+                        fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_out=rc, u_zero=True, **kw)), 2.25 * w, 2
+                    elif mode == "defect" and dn == "f64":
+                        e32 = empty_field(n, n, torch.float32); r32 = empty_field(n, n, torch.float32)
+                        fn = (lambda: ops.vc_defect_pass(u, out, f, h, h, e_in=e32, r_out=r32, sumsq_out=ss, **kw))
+                        byt, sw = 32.0, 0
                     elif mode == "resrestrict":
                         fn, byt, sw = (lambda: ops.vc_pass(u, None, f, h, h, sweeps=0, coarse_out=rc, **kw)), 2.25 * w, 0
                     else:
