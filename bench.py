@@ -54,6 +54,7 @@ def parse():
                          "evaluating f - A u in fp64 has a rounding floor of ~eps*8/h^2*|u| = 3e-8 at h = 1/16384")
     ap.add_argument("--cpu-n", type=int, default=4097, help="grid of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
@@ -210,6 +211,10 @@ def gpu_arm(a):
         line = run_distributed_bench(a, world, rank, dev, peak, peak_src, ClockSampler)
         if rank == 0:
             print(json.dumps(line), flush=True)
+        import gc
+        gc.collect()  # captured graphs hold NCCL work: make sure they are gone before the communicator
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
         return
 

@@ -217,6 +217,7 @@ class DistributedCycleEngine:
         self.D = self.part.dist_levels
         self.be = backend if backend is not None else DeviceBackend(device)
         self._bufs: Dict[Tuple[int, torch.dtype], _Bufs] = {}
+        self.valid: Dict[int, int] = {}  # data_ptr -> number of ghost rows per side that currently hold exact values
         an, am = self.part.agg_shape
         self.coarse = self.be.make_coarse_engine(an, am, self.domain, num_levels - self.D, cycle_type, pre, post,
                                                  coarse_tolerance, coarse_max_iterations)
@@ -229,15 +230,19 @@ class DistributedCycleEngine:
         return mine + ([b for lv in inner.levels for b in lv._bufs.values()] if inner is not None else [])
 
     def buffer_state(self):
-        return tuple(b.u.data_ptr() for b in self._all_bufs())
+        # roles AND ghost validity: a captured graph bakes in which exchanges were (not) needed
+        return tuple((b.u.data_ptr(), self.vdepth(b.u), self.vdepth(b.tmp), self.vdepth(b.f)) for b in self._all_bufs())
 
     def snapshot_roles(self):
-        return [(b, b.u, b.tmp) for b in self._all_bufs()]
+        # buffer roles + ghost-validity bookkeeping: both must be re-applied after a graph replay, which runs no
+        # Python and therefore updates neither
+        return ([(b, b.u, b.tmp) for b in self._all_bufs()], dict(self.valid), self.exchanges)
 
-    @staticmethod
-    def restore_roles(snap) -> None:
-        for b, u, tmp in snap:
+    def restore_roles(self, snap) -> None:
+        roles, valid, _ = snap
+        for b, u, tmp in roles:
             b.u, b.tmp = u, tmp
+        self.valid = dict(valid)
 
     # -- buffers ------------------------------------------------------------------------------------------
     def bufs(self, l: int, dtype) -> _Bufs:
@@ -252,32 +257,52 @@ class DistributedCycleEngine:
 
     # -- communication ------------------------------------------------------------------------------------
     def exchange(self, t: torch.Tensor, l: int) -> None:
-        """Refresh the ghost rows of a level-l local array from the neighbouring slabs."""
-        if self.world == 1:
+        """Refresh the ghost rows of one level-l local array from the neighbouring slabs."""
+        self.exchange_many([(t, l)])
+
+    def exchange_many(self, items) -> None:
+        """Refresh the ghost rows of several (array, level) pairs with ONE grouped send/recv launch."""
+        for t, l in items:
+            self.valid[t.data_ptr()] = self.part.ghost
+        if self.world == 1 or not items:
             return
-        s = self.part.slab(l)
         G = self.part.ghost
-        lo, hi = s.own_local
-        ops_ = []
-        keep = []
-        if s.g_lo:  # lower neighbour (rank - 1)
-            send = t[lo:lo + G].contiguous() if not _rows_contiguous(t) else _rows(t, lo, lo + G)
-            recv = _rows(t, 0, s.g_lo) if _rows_contiguous(t) else torch.empty_like(t[0:s.g_lo])
-            ops_ += [dist.P2POp(dist.isend, send, self._peer(self.rank - 1), self.group),
-                     dist.P2POp(dist.irecv, recv, self._peer(self.rank - 1), self.group)]
-            keep.append((recv, 0, s.g_lo))
-        if s.g_hi:  # upper neighbour (rank + 1)
-            send = t[hi - G:hi].contiguous() if not _rows_contiguous(t) else _rows(t, hi - G, hi)
-            recv = _rows(t, hi, hi + s.g_hi) if _rows_contiguous(t) else torch.empty_like(t[hi:hi + s.g_hi])
-            ops_ += [dist.P2POp(dist.isend, send, self._peer(self.rank + 1), self.group),
-                     dist.P2POp(dist.irecv, recv, self._peer(self.rank + 1), self.group)]
-            keep.append((recv, hi, hi + s.g_hi))
+        ops_, fix = [], []
+        for t, l in items:
+            s = self.part.slab(l)
+            lo, hi = s.own_local
+            contiguous = _rows_contiguous(t)
+            for has, peer, send_rows, recv_rows in ((s.g_lo, self.rank - 1, (lo, lo + G), (0, s.g_lo)),
+                                                    (s.g_hi, self.rank + 1, (hi - G, hi), (hi, hi + s.g_hi))):
+                if not has:
+                    continue
+                send = _rows(t, *send_rows) if contiguous else t[send_rows[0]:send_rows[1]].contiguous()
+                recv = _rows(t, *recv_rows) if contiguous else torch.empty_like(t[recv_rows[0]:recv_rows[1]])
+                ops_ += [dist.P2POp(dist.isend, send, self._peer(peer), self.group),
+                         dist.P2POp(dist.irecv, recv, self._peer(peer), self.group)]
+                if not contiguous:
+                    fix.append((t, recv, recv_rows))
         for w in dist.batch_isend_irecv(ops_):
             w.wait()
-        if not _rows_contiguous(t):
-            for recv, a, b in keep:
-                t[a:b].copy_(recv)
+        for t, recv, (a, b) in fix:
+            t[a:b].copy_(recv)
         self.exchanges += 1
+
+    # -- ghost validity bookkeeping: exchange only when the next pass needs deeper valid ghosts than it has ------
+    def vdepth(self, t: Optional[torch.Tensor]) -> int:
+        return self.part.ghost if t is None else self.valid.get(t.data_ptr(), 0)
+
+    def set_valid(self, t: torch.Tensor, depth: int) -> None:
+        self.valid[t.data_ptr()] = max(0, min(self.part.ghost, depth))
+
+    def ensure(self, need: int, items, effective=None) -> None:
+        """`items`: (array, level) inputs of the next pass, `effective(depths) -> fine-row validity`.
+        If the inputs do not provide `need` valid ghost rows, every input that is not fully valid is
+        refreshed in one batch."""
+        depths = [self.vdepth(t) for t, _ in items]
+        have = effective(depths) if effective is not None else min(depths)
+        if have < need:
+            self.exchange_many([(t, l) for (t, l), d in zip(items, depths) if d < self.part.ghost])
 
     def _peer(self, r: int) -> int:
         return r if self.group is None else dist.get_global_rank(self.group, r)
@@ -311,6 +336,7 @@ class DistributedCycleEngine:
                 cb.f[self.world * per].copy_(chunks[self.world - 1][per, :ny])
         full_u = self.coarse.cycle(dtype, u_zero)
         b.u.copy_(full_u[s.row0:s.row0 + s.loc_nx])
+        self.set_valid(b.u, self.part.ghost)  # cut out of the full correction: every ghost row is exact
 
     # -- the recursion ----------------------------------------------------------------------------------------
     def _reps(self, l: int) -> int:
@@ -330,18 +356,28 @@ class DistributedCycleEngine:
         s = self.part.slab(l)
         b, c = self.bufs(l, dtype), self.bufs(l + 1, dtype)
         off, rows = self.part.coarse_view(l)
+        G = self.part.ghost
+        # down: `pre` sweeps + residual + restriction; dependency cone of the owned coarse rows = 2*pre + 2 fine rows
+        ins = [(b.f, l)] + ([] if u_zero else [(b.u, l)])
+        self.ensure(2 * self.pre + 2, ins)
+        v = min(self.vdepth(t) for t, _ in ins)
         self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.pre, coefficient=-1.0, coarse_out=c.f[off:off + rows],
                         u_zero=u_zero)
         b.u, b.tmp = b.tmp, b.u
-        self.exchange(b.u, l)
-        if l + 1 < self.D:
-            self.exchange(c.f, l + 1)  # the agglomerated level gathers owned rows only
+        self.set_valid(b.u, v - 2 * self.pre)
+        self.set_valid(c.f, (v - (2 * self.pre + 2)) // 2)
         for rep in range(self._reps(l)):
             self.cycle(dtype, l + 1, u_zero=(rep == 0))
+        # up: prolongation + `post` sweeps (+ norm): cone 2*post (+1); the prolongation of a coarse field with v_c
+        # valid ghost rows is exact on 2*v_c - 1 fine ghost rows
+        norm = sumsq_out is not None and l == 0
+        self.ensure(2 * self.post + (1 if norm else 0), [(b.u, l), (b.f, l), (c.u, l + 1)],
+                    effective=lambda d: min(d[0], d[1], 2 * d[2] - 1))
+        v = min(self.vdepth(b.u), self.vdepth(b.f), 2 * self.vdepth(c.u) - 1)
         self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.post, coefficient=-1.0, coarse_in=c.u[off:off + rows],
-                        sumsq_out=sumsq_out if l == 0 else None, norm_rows=s.own_local)
+                        sumsq_out=sumsq_out if norm else None, norm_rows=s.own_local)
         b.u, b.tmp = b.tmp, b.u
-        self.exchange(b.u, l)
+        self.set_valid(b.u, v - 2 * self.post)
 
     # -- data movement helpers -----------------------------------------------------------------------------------
     def scatter_rows(self, dst: torch.Tensor, full_rows_fn, l: int = 0) -> None:
@@ -414,6 +450,7 @@ class DistributedMixedPrecisionSolver:
         s = self.s0
         src = torch.as_tensor(f_global)[s.row0:s.row0 + s.loc_nx]
         b.f.copy_(src)
+        self.eng.set_valid(b.f, self.eng.part.ghost)
 
     def set_rhs_sinsin_device(self, amplitude: float = 2 * math.pi ** 2) -> None:
         """Manufactured f = amplitude*sin(pi x) sin(pi y) generated in HBM on the slab (global coordinates)."""
@@ -424,6 +461,7 @@ class DistributedMixedPrecisionSolver:
         xa = x0 + s.row0 * s.hx
         xb = x0 + (s.row0 + s.loc_nx - 1) * s.hx
         ops.fill_sinsin_(b.f, (xa, xb, y0, y1), amplitude, 1.0, 1.0)
+        self.eng.set_valid(b.f, self.eng.part.ghost)  # generated on the ghost rows as well
 
     def zero_boundary_ring_of_rhs(self) -> None:
         b = self.eng.bufs(0, torch.float64)
@@ -440,6 +478,7 @@ class DistributedMixedPrecisionSolver:
         eng = self.eng
         b64 = eng.bufs(0, torch.float64)
         b64.u.zero_()
+        eng.set_valid(b64.u, eng.part.ghost)
         self.phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
         self.history: List[float] = []
         if self.phase == "refine":
@@ -448,6 +487,8 @@ class DistributedMixedPrecisionSolver:
             b32 = eng.bufs(0, torch.float32)
             b32.f.copy_(b64.f)
             b32.u.zero_()
+            eng.set_valid(b32.f, eng.vdepth(b64.f))
+            eng.set_valid(b32.u, eng.part.ghost)
         return float("nan")
 
     def _norm(self, slot: int) -> float:
@@ -462,14 +503,18 @@ class DistributedMixedPrecisionSolver:
         b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
         self.ss.zero_()
         if with_update:
+            eng.ensure(1, [(b64.u, 0), (b32.u, 0), (b64.f, 0)])
+            v = min(eng.vdepth(b64.u), eng.vdepth(b32.u))
             eng.be.vc_defect_pass(b64.u, b64.tmp, b64.f, s.hx, s.hy, e_in=b32.u, r_out=b32.f, sumsq_out=self.ss[1:2],
                                   norm_rows=s.own_local)
             b64.u, b64.tmp = b64.tmp, b64.u
-            eng.exchange(b64.u, 0)
+            eng.set_valid(b64.u, v)
         else:
+            eng.ensure(1, [(b64.u, 0), (b64.f, 0)])
+            v = eng.vdepth(b64.u)
             eng.be.vc_defect_pass(b64.u, None, b64.f, s.hx, s.hy, r_out=b32.f, sumsq_out=self.ss[1:2],
                                   norm_rows=s.own_local)
-        eng.exchange(b32.f, 0)
+        eng.set_valid(b32.f, min(v, eng.vdepth(b64.f)) - 1)
         eng.allreduce_sum(self.ss)
 
     def _launch_refine(self) -> None:
@@ -524,7 +569,8 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
-                                          device=dev, use_cuda_graphs=not a.no_graphs)
+                                          device=dev, use_cuda_graphs=not a.no_graphs,
+                                          **({"agglomerate_below": a.agg} if getattr(a, "agg", None) else {}))
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
     sol.eng.exchange(sol.eng.bufs(0, torch.float64).f, 0)

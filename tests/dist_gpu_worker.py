@@ -21,17 +21,24 @@ def main():
     g = O.OGrid(nx, ny, dom)
     x, y = g.coords()
     f = 2 * np.pi ** 2 * np.sin(np.pi * x)[:, None] * np.sin(np.pi * y)[None, :]
+    import time
     res = {}
+    t00 = time.time()
     for strategy in ("double", "adaptive", "adaptive_graphs"):
         sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy.split("_")[0],
                                               tolerance=1e-8, agglomerate_below=129, device=dev,
                                               use_cuda_graphs=strategy.endswith("graphs"))
         sol.set_rhs_from_global(torch.from_numpy(f).to(dev))
+        print(f"[worker r{dist.get_rank()}] {strategy}: start solve at {time.time() - t00:.1f}s D={sol.eng.D}", file=sys.stderr, flush=True)
         u, info = sol.solve()
+        print(f"[worker r{dist.get_rank()}] {strategy}: solve done at {time.time() - t00:.1f}s it={info['iterations']} ex={sol.eng.exchanges}", file=sys.stderr, flush=True)
         if strategy.endswith("graphs"):  # second and third solve replay captured graphs (NCCL send/recv included)
             u, info = sol.solve()
             u, info = sol.solve()
             res["graphs_captured"] = sol.graphs.captured
+        if dist.get_rank() == 0:
+            print(f"[worker] {strategy}: solved in {time.time() - t00:.1f}s since start, {info['iterations']} cycles, "
+                  f"graphs={sol.graphs.captured}", file=sys.stderr, flush=True)
         full = sol.eng.gather_solution(u)
         res[strategy] = {"iterations": info["iterations"], "history": info["residual_history"],
                          "u": full.cpu().numpy()}
@@ -39,6 +46,12 @@ def main():
         res["D"] = sol.eng.D
     if dist.get_rank() == 0:
         torch.save(res, sys.argv[1])
+    # captured graphs hold NCCL work: release them before tearing the communicator down
+    del sol, u, full
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 

@@ -70,6 +70,7 @@ def _worker(rank, world, port, case, out):
             b = eng.bufs(0, torch.float64)
             s = eng.part.slab(0)
             b.f.copy_(torch.from_numpy(f[s.row0:s.row0 + s.loc_nx]))
+            eng.set_valid(b.f, GHOST)  # filled from the global array, ghost rows included
             ss = torch.zeros(1, dtype=torch.float64)
             norms = []
             for _ in range(case["cycles"]):
