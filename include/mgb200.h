@@ -154,6 +154,19 @@ MG_API int mg_maxerr_sinsin(const void* u, int nx, int ny, int64_t ld, double x0
                      double y1, double amplitude, double kx, double ky, int dtype, double* workspace,
                      double* out, void* stream);
 
+/* Helmholtz-shifted variants: operator coefficient*lap_h + shift (shift >= 0), i.e. (-lap + lambda) u = f for
+ * coefficient = -1: the implicit heat step (I - alpha*dt*lap) u = rhs of docs/methodology.md:710 divided by
+ * alpha*dt (the shifted stencil exists only in applications/heat_equation.py:459-497 of the reference, which
+ * solves it with plain GS).  The smoother relaxes (-lap_h + shift) u = f.  shift = 0 reproduces the functions above. */
+MG_API int mg_residual_h(const void* u, const void* f, void* r, int nx, int ny, int64_t ld_u, int64_t ld_f,
+                  int64_t ld_r, double hx, double hy, double coefficient, double shift, int dtype_in,
+                  int dtype_out, void* stream);
+MG_API int mg_smooth_rbgs_h(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx,
+                     double hy, double omega, double shift, int sweeps, int dtype, void* stream);
+MG_API int mg_coarse_solve_lexgs_h(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f,
+                            double hx, double hy, double omega, double coefficient, double shift,
+                            double tolerance, int max_iterations, double* info, int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused, temporally blocked V/W-cycle passes ("vector path": TMA-staged, 16-byte aligned fields)
  *
@@ -200,16 +213,18 @@ MG_API int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const
  * gpu/multi_gpu_solver.py:347-383): the field handed in is a slab of rows of a larger grid including its
  * ghost rows; the first / last local rows are treated like Dirichlet rows (they are ghost rows refreshed by
  * the halo exchange, or true boundary rows on the first / last rank).  nx may be even.  Only rows
- * [norm_row_lo, norm_row_hi) enter the residual sum (each rank sums the rows it owns; hi < 0: all). */
+ * [norm_row_lo, norm_row_hi) enter the residual sum (each rank sums the rows it owns; hi < 0: all).
+ * `shift` >= 0 adds the Helmholtz term (operator coefficient*lap_h + shift; 0 = Poisson). */
 MG_API int mg_vc_pass_slab(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
                     double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
                     int64_t ld_f, int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega,
                     double coefficient, int sweeps, int dtype, int flags, int norm_row_lo, int norm_row_hi,
-                    void* stream);
+                    double shift, void* stream);
 MG_API int mg_vc_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
                            double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in,
                            int64_t ld_out, int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy,
-                           double coefficient, int flags, int norm_row_lo, int norm_row_hi, void* stream);
+                           double coefficient, int flags, int norm_row_lo, int norm_row_hi, double shift,
+                           void* stream);
 
 /* `sweeps` temporally blocked RB-GS sweeps in one HBM pass (replaces GaussSeidelSmoother(red_black=True)
  * .smooth, smoothers.py:117-151; SmoothingKernels.red_black_gauss_seidel / block_gauss_seidel_kernel,

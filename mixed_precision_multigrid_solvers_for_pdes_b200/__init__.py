@@ -6,7 +6,9 @@ Drop-in for the reference's ``multigrid.core`` / ``.operators`` / ``.solvers`` s
 from . import ops
 from ._lib import LIB_PATH, MGLibraryError
 from .core import Grid, PrecisionLevel, PrecisionManager
-from .operators import BaseOperator, LaplacianOperator, ProlongationOperator, RestrictionOperator
+from .applications.heat_solver import HeatSolver2D
+from .operators import (BaseOperator, HelmholtzOperator, LaplacianOperator, ProlongationOperator,
+                        RestrictionOperator)
 from .problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
                        TimeSteppingMethod)
 from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
@@ -15,7 +17,7 @@ from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, Ba
 __version__ = "0.1.0"
 GPU_AVAILABLE = True  # the only path there is
 
-__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "RestrictionOperator",
+__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "HeatSolver2D", "RestrictionOperator",
            "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
            "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
            "SymmetricGaussSeidelSmoother", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",

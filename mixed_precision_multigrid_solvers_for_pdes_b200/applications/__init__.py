@@ -1,0 +1,6 @@
+from ..problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
+                        TimeSteppingMethod)
+from .heat_solver import HeatSolver2D
+
+__all__ = ["HeatSolver2D", "HeatProblem", "TimeSteppingConfig", "TimeSteppingMethod", "PoissonProblem",
+           "PoissonTestProblems", "HeatTestProblems"]

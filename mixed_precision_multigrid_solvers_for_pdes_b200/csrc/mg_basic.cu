@@ -374,31 +374,43 @@ int mg_apply_laplacian(const void* u, void* out, int nx, int ny, int64_t ld_u, i
 
 int mg_residual(const void* u, const void* f, void* r, int nx, int ny, int64_t ld_u, int64_t ld_f, int64_t ld_r,
                 double hx, double hy, double coefficient, int dtype_in, int dtype_out, void* stream) {
+  return mg_residual_h(u, f, r, nx, ny, ld_u, ld_f, ld_r, hx, hy, coefficient, 0.0, dtype_in, dtype_out, stream);
+}
+
+int mg_residual_h(const void* u, const void* f, void* r, int nx, int ny, int64_t ld_u, int64_t ld_f, int64_t ld_r,
+                  double hx, double hy, double coefficient, double shift, int dtype_in, int dtype_out, void* stream) {
   MG_REQUIRE(u && f && r && nx >= 3 && ny >= 3 && ld_u >= ny && ld_f >= ny && ld_r >= ny && hx > 0 && hy > 0);
+  MG_REQUIRE(shift >= 0.0);
   if (!valid_dtype(dtype_in) || !valid_dtype(dtype_out)) return MG_ERR_DTYPE;
   const dim3 g = grid2d(nx, ny), b(BX, BY);
   cudaStream_t st = as_stream(stream);
   if (dtype_in == MG_F64 && dtype_out == MG_F64)
     residual_kernel<double, double, double><<<g, b, 0, st>>>((const double*)u, (const double*)f, (double*)r, nx, ny,
                                                              ld_u, ld_f, ld_r,
-                                                             make_scalars<double>(hx, hy, 1.0, coefficient));
+                                                             make_scalars<double>(hx, hy, 1.0, coefficient, shift));
   else if (dtype_in == MG_F32 && dtype_out == MG_F32)
     residual_kernel<float, float, float><<<g, b, 0, st>>>((const float*)u, (const float*)f, (float*)r, nx, ny, ld_u,
-                                                          ld_f, ld_r, make_scalars<float>(hx, hy, 1.0, coefficient));
+                                                          ld_f, ld_r, make_scalars<float>(hx, hy, 1.0, coefficient, shift));
   else if (dtype_in == MG_F32 && dtype_out == MG_F64)
     residual_kernel<float, double, double><<<g, b, 0, st>>>((const float*)u, (const float*)f, (double*)r, nx, ny,
                                                             ld_u, ld_f, ld_r,
-                                                            make_scalars<double>(hx, hy, 1.0, coefficient));
+                                                            make_scalars<double>(hx, hy, 1.0, coefficient, shift));
   else
     residual_kernel<double, float, double><<<g, b, 0, st>>>((const double*)u, (const double*)f, (float*)r, nx, ny,
                                                             ld_u, ld_f, ld_r,
-                                                            make_scalars<double>(hx, hy, 1.0, coefficient));
+                                                            make_scalars<double>(hx, hy, 1.0, coefficient, shift));
   return check_launch("mg_residual");
 }
 
 int mg_smooth_rbgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
                    double omega, int sweeps, int dtype, void* stream) {
+  return mg_smooth_rbgs_h(u, f, nx, ny, ld_u, ld_f, hx, hy, omega, 0.0, sweeps, dtype, stream);
+}
+
+int mg_smooth_rbgs_h(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
+                     double omega, double shift, int sweeps, int dtype, void* stream) {
   MG_REQUIRE(u && f && nx >= 3 && ny >= 3 && ld_u >= ny && ld_f >= ny && hx > 0 && hy > 0 && sweeps >= 0);
+  MG_REQUIRE(shift >= 0.0);
   if (!valid_dtype(dtype)) return MG_ERR_DTYPE;
   const int nj = (ny - 2 + 1) / 2;  // max points of one colour in a row
   const dim3 g((nj + BX - 1) / BX, (nx - 2 + BY - 1) / BY), b(BX, BY);
@@ -407,10 +419,10 @@ int mg_smooth_rbgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t
     for (int colour = 0; colour < 2; ++colour) {
       if (dtype == MG_F64)
         rbgs_colour_kernel<double><<<g, b, 0, st>>>((double*)u, (const double*)f, nx, ny, ld_u, ld_f, colour,
-                                                    make_scalars<double>(hx, hy, omega, 1.0));
+                                                    make_scalars<double>(hx, hy, omega, 1.0, shift));
       else
         rbgs_colour_kernel<float><<<g, b, 0, st>>>((float*)u, (const float*)f, nx, ny, ld_u, ld_f, colour,
-                                                   make_scalars<float>(hx, hy, omega, 1.0));
+                                                   make_scalars<float>(hx, hy, omega, 1.0, shift));
     }
   return check_launch("mg_smooth_rbgs", 2 * sweeps);
 }
@@ -461,7 +473,15 @@ int mg_smooth_lexgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_
 int mg_coarse_solve_lexgs(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
                           double omega, double coefficient, double tolerance, int max_iterations, double* info,
                           int dtype, void* stream) {
+  return mg_coarse_solve_lexgs_h(u, f, nx, ny, ld_u, ld_f, hx, hy, omega, coefficient, 0.0, tolerance, max_iterations,
+                                 info, dtype, stream);
+}
+
+int mg_coarse_solve_lexgs_h(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
+                            double omega, double coefficient, double shift, double tolerance, int max_iterations,
+                            double* info, int dtype, void* stream) {
   MG_REQUIRE(u && f && nx >= 3 && ny >= 3 && ld_u >= ny && ld_f >= ny && hx > 0 && hy > 0 && max_iterations >= 1);
+  MG_REQUIRE(shift >= 0.0);
   if (!valid_dtype(dtype)) return MG_ERR_DTYPE;
   const int diag = (nx < ny ? nx : ny) - 2;
   int threads = 32;
@@ -472,7 +492,7 @@ int mg_coarse_solve_lexgs(void* u, const void* f, int nx, int ny, int64_t ld_u, 
   cudaStream_t st = as_stream(stream);
   const double hxhy = hx * hy;
   if (dtype == MG_F64) {
-    auto s = make_scalars<double>(hx, hy, omega, coefficient);
+    auto s = make_scalars<double>(hx, hy, omega, coefficient, shift);
     if (use_smem)
       coarse_solve_kernel<double, true><<<1, threads, smem, st>>>((double*)u, (const double*)f, nx, ny, ld_u, ld_f,
                                                                   hxhy, tolerance, max_iterations, info, s);
@@ -480,7 +500,7 @@ int mg_coarse_solve_lexgs(void* u, const void* f, int nx, int ny, int64_t ld_u, 
       coarse_solve_kernel<double, false><<<1, threads, 0, st>>>((double*)u, (const double*)f, nx, ny, ld_u, ld_f,
                                                                 hxhy, tolerance, max_iterations, info, s);
   } else {
-    auto s = make_scalars<float>(hx, hy, omega, coefficient);
+    auto s = make_scalars<float>(hx, hy, omega, coefficient, shift);
     if (use_smem)
       coarse_solve_kernel<float, true><<<1, threads, smem, st>>>((float*)u, (const float*)f, nx, ny, ld_u, ld_f,
                                                                  hxhy, tolerance, max_iterations, info, s);

@@ -35,18 +35,20 @@ template <typename T> struct StencilScalars {
   T omega;     // relaxation parameter
   T one_minus_omega;  // (1 - omega)         (smoothers.py:193)
   T coeff;     // LaplacianOperator.coefficient
+  T shift;     // Helmholtz shift lambda >= 0: operator coeff*lap_h + lambda (0 for the reference's Poisson path)
   // reciprocal forms for the fast (vector/fused) kernels
   T ihx2, ihy2, inv_neg_diag;
 };
 
 template <typename T>
-inline StencilScalars<T> make_scalars(double hx, double hy, double omega, double coeff) {
+inline StencilScalars<T> make_scalars(double hx, double hy, double omega, double coeff, double shift = 0.0) {
   StencilScalars<T> s;
   const double hx2 = pow(hx, 2.0), hy2 = pow(hy, 2.0);  // same libm pow CPython's float ** uses
   const double diag = -2.0 / hx2 - 2.0 / hy2;
   s.hx2 = (T)hx2;
   s.hy2 = (T)hy2;
-  s.neg_diag = (T)(-diag);
+  s.neg_diag = (T)(-diag + shift);  // diagonal of -lap_h + lambda
+  s.shift = (T)shift;
   s.cc = (T)(2.0 / hx2 + 2.0 / hy2);
   s.omega = (T)omega;
   s.one_minus_omega = (T)(1 - omega);
@@ -71,7 +73,8 @@ template <typename T>
 __device__ __forceinline__ T apply_strict(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf) {
   using A = Strict<T>;
   const T t = A::sub(A::add(A::div(A::add(up, dn), s.hx2), A::div(A::add(rt, lf), s.hy2)), A::mul(uc, s.cc));
-  return A::mul(s.coeff, t);
+  const T au = A::mul(s.coeff, t);
+  return s.shift != (T)0 ? A::add(au, A::mul(s.shift, uc)) : au;
 }
 
 // ------------------------------------------------------------------------------------------

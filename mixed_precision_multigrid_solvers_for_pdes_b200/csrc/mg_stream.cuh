@@ -153,7 +153,7 @@ template <typename T>
 __device__ __forceinline__ T residual_fast(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
   T t = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
   t = fma(-uc, s.cc, t);
-  return fma(-s.coeff, t, f);
+  return fma(-s.shift, uc, fma(-s.coeff, t, f));  // exact no-op for shift = 0
 }
 
 // Isotropic (hx == hy), unrelaxed (omega == 1) specialisation: 5 instead of 8 instructions per point.
@@ -168,7 +168,7 @@ template <typename T>
 __device__ __forceinline__ T residual_iso(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
   const T sum = (up + dn) + (rt + lf);
   const T t = fma((T)-4, uc, sum);  // h^2 * lap_h u
-  return fma(-s.coeff * s.ihx2, t, f);
+  return fma(-s.shift, uc, fma(-s.coeff * s.ihx2, t, f));
 }
 template <bool SIMPLE, typename T>
 __device__ __forceinline__ T relax_sel(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {

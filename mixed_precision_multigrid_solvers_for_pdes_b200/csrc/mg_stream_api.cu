@@ -79,13 +79,13 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
                     int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_ci, int64_t ld_co, int64_t ld_fi,
                     int64_t ld_ro, double hx, double hy, double omega, double coefficient, int sweeps, int dtype,
                     int front, int back, int flags, void* stream, const char* what, int norm_lo = 0,
-                    int norm_hi = -1) {
+                    int norm_hi = -1, double shift = 0.0) {
   const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
   const bool store = (flags & MG_VC_NO_STORE) == 0;
   const bool u_zero = (flags & MG_VC_U_ZERO) != 0;
   const int rows_override = (flags >> 8) & 0xFFF;
   if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
-  if (!f || nx < 3 || ny < 3 || ld_f < ny || hx <= 0 || hy <= 0) return MG_ERR_BADARG;
+  if (!f || nx < 3 || ny < 3 || ld_f < ny || hx <= 0 || hy <= 0 || !(shift >= 0.0)) return MG_ERR_BADARG;
   if (!u_zero && (!u_in || ld_in < ny)) return MG_ERR_BADARG;
   if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
   if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
@@ -142,11 +142,11 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   const bool simple = (omega == 1.0) && (hx == hy);  // isotropic, unrelaxed: the 5-instruction point update
   int rc;
   if (dtype == MG_F64) {
-    auto sc = make_scalars<double>(hx, hy, omega, coefficient);
+    auto sc = make_scalars<double>(hx, hy, omega, coefficient, shift);
     rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, simple, m, p, sc, st)
              : launch_pass_f64_tma(sweeps, front, back, simple, m, p, sc, st);
   } else {
-    auto sc = make_scalars<float>(hx, hy, omega, coefficient);
+    auto sc = make_scalars<float>(hx, hy, omega, coefficient, shift);
     rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, simple, m, p, sc, st)
              : launch_pass_f32_tma(sweeps, front, back, simple, m, p, sc, st);
   }
@@ -183,26 +183,26 @@ int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* coarse_
 int mg_vc_pass_slab(const void* u_in, void* u_out, const void* f, const void* coarse_in, void* coarse_out,
                     double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
                     int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega, double coefficient, int sweeps,
-                    int dtype, int flags, int norm_row_lo, int norm_row_hi, void* stream) {
+                    int dtype, int flags, int norm_row_lo, int norm_row_hi, double shift, void* stream) {
   if ((flags & MG_VC_RESTRICT) && (flags & MG_VC_NORM)) return MG_ERR_UNSUPPORTED;
   const int front = (flags & MG_VC_PROLONG) ? FRONT_PROLONG : FRONT_NONE;
   const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
   return run_pass(u_in, u_out, f, coarse_in, coarse_out, nullptr, nullptr, sumsq_out, workspace, nx, ny, ld_in, ld_out,
                   ld_f, ld_ci, ld_co, 0, 0, hx, hy, omega, coefficient, sweeps, dtype, front, back, flags, stream,
-                  "mg_vc_pass_slab", norm_row_lo, norm_row_hi);
+                  "mg_vc_pass_slab", norm_row_lo, norm_row_hi, shift);
 }
 
 int mg_vc_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
                            double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
                            int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy, double coefficient, int flags,
-                           int norm_row_lo, int norm_row_hi, void* stream) {
+                           int norm_row_lo, int norm_row_hi, double shift, void* stream) {
   const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
   const int back = r_out ? BACK_RESID : BACK_NONE;
   int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_U_ZERO);
   if (!e_in) fl |= MG_VC_NO_STORE;
   return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
                   workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,
-                  back, fl, stream, "mg_vc_defect_pass_slab", norm_row_lo, norm_row_hi);
+                  back, fl, stream, "mg_vc_defect_pass_slab", norm_row_lo, norm_row_hi, shift);
 }
 
 int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out, double* sumsq_out,

@@ -1,5 +1,5 @@
 from .base import BaseOperator
-from .laplacian import LaplacianOperator
+from .laplacian import HelmholtzOperator, LaplacianOperator
 from .transfer import ProlongationOperator, RestrictionOperator
 
-__all__ = ["BaseOperator", "LaplacianOperator", "RestrictionOperator", "ProlongationOperator"]
+__all__ = ["BaseOperator", "LaplacianOperator", "HelmholtzOperator", "RestrictionOperator", "ProlongationOperator"]

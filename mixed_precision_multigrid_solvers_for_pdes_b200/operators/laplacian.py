@@ -60,3 +60,36 @@ class LaplacianOperator(BaseOperator):
     def condition_number(self, grid) -> float:
         ev = self.eigenvalues_1d(min(grid.nx - 2, grid.ny - 2), max(grid.hx, grid.hy))
         return float(np.abs(ev[-1] / ev[0]))
+
+
+class HelmholtzOperator(LaplacianOperator):
+    """coefficient * lap_h(u) + shift * u  (shift >= 0).  With coefficient = -1 this is -lap + lambda, the operator of
+    an implicit heat step: (I - alpha*dt*lap) u = rhs  <=>  (-lap + 1/(alpha*dt)) u = rhs/(alpha*dt)
+    (docs/methodology.md:710; the reference has the shifted stencil only inside applications/heat_equation.py:459-497,
+    solved there with plain Gauss-Seidel).  The smoothers relax (-lap_h + shift) u = rhs when the cycle engine sees
+    this operator."""
+
+    def __init__(self, coefficient: float = -1.0, shift: float = 0.0):
+        super().__init__(coefficient)
+        if shift < 0:
+            raise ValueError("shift must be >= 0")
+        self.shift = float(shift)
+        self.name = f"Helmholtz(coeff={coefficient}, shift={shift})"
+
+    def apply(self, grid, field=None):
+        if field is None:
+            field = grid.values
+        self._check(grid, field)
+        d, was_np = to_device(field)
+        out = ops.apply_laplacian(d, grid.hx, grid.hy, self.coefficient)
+        if self.shift:
+            out[1:-1, 1:-1] += self.shift * d[1:-1, 1:-1]
+        return like_input(out, was_np)
+
+    def residual(self, grid, u, f):
+        self._check(grid, u)
+        du, was_np = to_device(u)
+        df, _ = to_device(f, dtype=du.dtype)
+        r = like_input(ops.residual(du, df, grid.hx, grid.hy, self.coefficient, shift=self.shift), was_np)
+        grid.residual = r.copy() if was_np else r
+        return r

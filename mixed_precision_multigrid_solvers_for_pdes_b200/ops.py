@@ -42,22 +42,23 @@ def apply_laplacian(u: torch.Tensor, hx: float, hy: float, coefficient: float = 
 
 
 def residual(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, coefficient: float = 1.0,
-             out: Optional[torch.Tensor] = None, out_dtype=None) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, out_dtype=None, shift: float = 0.0) -> torch.Tensor:
     _check_same_shape(u, f, "residual")
     if u.dtype != f.dtype:
         raise TypeError("residual: u and f must share a dtype")
     nx, ny = u.shape
     if out is None:
         out = empty_field(nx, ny, out_dtype or u.dtype, u.device, zero=False)
-    _lib.call("mg_residual", u.data_ptr(), f.data_ptr(), out.data_ptr(), nx, ny, ld(u), ld(f), ld(out), hx, hy,
-              coefficient, code(u.dtype), code(out.dtype), stream_ptr())
+    _lib.call("mg_residual_h", u.data_ptr(), f.data_ptr(), out.data_ptr(), nx, ny, ld(u), ld(f), ld(out), hx, hy,
+              coefficient, shift, code(u.dtype), code(out.dtype), stream_ptr())
     return out
 
 
-def smooth_rbgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0, sweeps: int = 1):
+def smooth_rbgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0, sweeps: int = 1,
+                 shift: float = 0.0):
     _check_same_shape(u, f, "smooth_rbgs")
     nx, ny = u.shape
-    _lib.call("mg_smooth_rbgs", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, sweeps,
+    _lib.call("mg_smooth_rbgs_h", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, shift, sweeps,
               code(u.dtype), stream_ptr())
     return u
 
@@ -87,12 +88,12 @@ def smooth_lexgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega:
 
 def coarse_solve_lexgs_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, omega: float = 1.0,
                         coefficient: float = -1.0, tolerance: float = 1e-12, max_iterations: int = 1000,
-                        info: Optional[torch.Tensor] = None):
+                        info: Optional[torch.Tensor] = None, shift: float = 0.0):
     """`info`: optional device tensor of >= 2 float64 receiving (sweeps done, last norm)."""
     _check_same_shape(u, f, "coarse_solve")
     nx, ny = u.shape
-    _lib.call("mg_coarse_solve_lexgs", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, coefficient,
-              tolerance, max_iterations, info.data_ptr() if info is not None else None, code(u.dtype), stream_ptr())
+    _lib.call("mg_coarse_solve_lexgs_h", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, omega, coefficient,
+              shift, tolerance, max_iterations, info.data_ptr() if info is not None else None, code(u.dtype), stream_ptr())
     return u
 
 
@@ -233,7 +234,7 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
             sweeps: int = 2, omega: float = 1.0, coefficient: float = -1.0,
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
             sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
-            u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None) -> None:
+            u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0) -> None:
     """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS sweeps -> [coarse_out = R(f - A u)] or
     [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored).
     ``u_zero``: treat u_in as identically zero without reading it."""
@@ -263,7 +264,7 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
               sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
               nx, ny, 0 if u_zero else ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
               ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
-              hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, nlo, nhi, stream_ptr())
+              hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, nlo, nhi, shift, stream_ptr())
     if timed:
         ev1.record()
         tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"rbgs{sweeps}"
@@ -283,7 +284,7 @@ def _loader_flag(loader: str) -> int:
 def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
                    e_in: Optional[torch.Tensor] = None, r_out: Optional[torch.Tensor] = None,
                    sumsq_out: Optional[torch.Tensor] = None, coefficient: float = -1.0, loader: str = "tma",
-                   rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None) -> None:
+                   rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0) -> None:
     """Mixed-precision defect-correction pass on the fp64 iterate (one HBM pass):
     u_out = u_in + e_in (fp32 correction; None: u unchanged, nothing stored), r_out = fp32(f - A u_out),
     sumsq_out[0] = sum of the squared fp64 residual."""
@@ -304,7 +305,7 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
               e_in.data_ptr() if e_in is not None else None, r_out.data_ptr() if r_out is not None else None,
               sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
               nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(e_in) if e_in is not None else 0,
-              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, stream_ptr())
+              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, shift, stream_ptr())
     if timed:
         ev1.record()
         TIMER.records.append((("update+" if e_in is not None else "") + ("resid32+N" if r_out is not None else "")

@@ -22,6 +22,9 @@ from .. import ops
 from ..device import empty_field, require_cuda, torch_dtype
 
 
+_NATIVE_OPERATORS = ("LaplacianOperator", "HelmholtzOperator")  # operators the kernels implement directly
+
+
 class _Buffers:
     __slots__ = ("u", "tmp", "f")
 
@@ -82,9 +85,14 @@ class CycleEngine:
         g = self.levels[lvl].grid
         sm = self.smoother
         kind = getattr(sm, "kind", "custom")
+        shift = getattr(self.operators[lvl], "shift", 0.0)
+        if shift and kind != "rbgs":
+            raise ValueError("a shifted (Helmholtz) operator is smoothed with red-black Gauss-Seidel only")
         if kind == "jacobi":
             ops.smooth_jacobi_(b.u, b.f, g.hx, g.hy, sm.omega, sweeps, tmp=b.tmp)
-        elif kind in ("rbgs", "lexgs", "sgs"):
+        elif kind == "rbgs":
+            ops.smooth_rbgs_(b.u, b.f, g.hx, g.hy, sm.omega, sweeps, shift=shift)
+        elif kind in ("lexgs", "sgs"):
             sm._smooth_device_(g, b.u, b.f, sweeps)
         else:  # foreign smoother object: use its public protocol on device tensors
             b.u.copy_(sm.smooth(g, self.operators[lvl], b.u, b.f, sweeps))
@@ -93,8 +101,8 @@ class CycleEngine:
         g = self.levels[lvl].grid
         op = self.operators[lvl]
         coeff = getattr(op, "coefficient", None)
-        if coeff is not None and type(op).__name__ == "LaplacianOperator":
-            return ops.residual(u, f, g.hx, g.hy, coeff, out=out)
+        if coeff is not None and type(op).__name__ in _NATIVE_OPERATORS:
+            return ops.residual(u, f, g.hx, g.hy, coeff, out=out, shift=getattr(op, "shift", 0.0))
         out.copy_(op.residual(g, u, f))
         return out
 
@@ -103,9 +111,9 @@ class CycleEngine:
         cs = self.coarse_solver
         op = self.operators[lvl]
         coeff = getattr(op, "coefficient", None)
-        if getattr(cs, "kind", None) == "lexgs" and coeff is not None and type(op).__name__ == "LaplacianOperator":
+        if getattr(cs, "kind", None) == "lexgs" and coeff is not None and type(op).__name__ in _NATIVE_OPERATORS:
             ops.coarse_solve_lexgs_(b.u, b.f, g.hx, g.hy, cs.omega, coeff, cs.tolerance, cs.max_iterations,
-                                    info=self.coarse_info)
+                                    info=self.coarse_info, shift=getattr(op, "shift", 0.0))
         else:  # any other IterativeSolver: its own solve loop (host-checked convergence)
             sol, _ = cs.solve(g, op, b.f, b.u, precision_manager)
             b.u.copy_(sol)
@@ -117,7 +125,7 @@ class CycleEngine:
         if self.kernels == "basic":
             return False
         op = self.operators[lvl]
-        ok = (getattr(self.smoother, "kind", None) == "rbgs" and type(op).__name__ == "LaplacianOperator"
+        ok = (getattr(self.smoother, "kind", None) == "rbgs" and type(op).__name__ in _NATIVE_OPERATORS
               and getattr(self.restriction_ops[lvl], "method", None) == "full_weighting"
               and getattr(self.prolongation_ops[lvl], "method", None) == "bilinear"
               and torch_dtype(level_dtypes[lvl]) == torch_dtype(level_dtypes[lvl + 1]))
@@ -141,22 +149,23 @@ class CycleEngine:
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
         coeff, omega, ld = self.operators[lvl].coefficient, self.smoother.omega, self.loader
+        sh = getattr(self.operators[lvl], "shift", 0.0)
         # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
         n = self.pre
         if u_zero and n == 0:
             b.u.zero_()  # nothing will overwrite the iterate before it is read
             u_zero = False
         while n > 2:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero, shift=sh)
             b.u, b.tmp = b.tmp, b.u
             n -= 2
             u_zero = False
         if n > 0:
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld,
-                        u_zero=u_zero)
+                        u_zero=u_zero, shift=sh)
             b.u, b.tmp = b.tmp, b.u
         else:
-            ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld)
+            ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld, shift=sh)
         # the coarse error equation starts from e = 0: the first coarse pass is told so instead of reading zeros
         for rep in range(self._reps(lvl)):
             self.cycle(level_dtypes, lvl + 1, precision_manager, u_zero=(rep == 0))
@@ -165,14 +174,14 @@ class CycleEngine:
         first = min(n, 2)
         last = (n - first) == 0
         ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, omega=omega, coefficient=coeff, coarse_in=c.u,
-                    sumsq_out=sumsq_out if last else None, loader=ld)
+                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh)
         b.u, b.tmp = b.tmp, b.u
         n -= first
         while n > 0:
             k = min(n, 2)
             n -= k
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, omega=omega, coefficient=coeff,
-                        sumsq_out=sumsq_out if n == 0 else None, loader=ld)
+                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh)
             b.u, b.tmp = b.tmp, b.u
 
     # -- the recursion ------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ import torch
 from .. import ops
 from ..core.grid import Grid
 from ..device import empty_field, like_input, require_cuda, to_device
-from ..operators.laplacian import LaplacianOperator
+from ..operators.laplacian import HelmholtzOperator, LaplacianOperator
 from ..operators.transfer import ProlongationOperator, RestrictionOperator
 from .engine import CycleEngine
 from .graphs import GraphCache
@@ -58,7 +58,7 @@ class MixedPrecisionMultigrid:
                  stagnation_ratio: float = 0.95, max_grid_size: Optional[int] = None,
                  gpu_memory_fraction: Optional[float] = None, min_precision: Optional[str] = None,
                  strict_reference_norm: bool = False, kernels: str = "auto", loader: str = "tma", device=None,
-                 use_cuda_graphs: bool = True, verbose: bool = False):
+                 use_cuda_graphs: bool = True, shift: float = 0.0, verbose: bool = False):
         key = str(precision_strategy).lower()
         if key not in _STRATEGIES:
             raise ValueError(f"Unknown precision strategy: {precision_strategy}")
@@ -87,6 +87,10 @@ class MixedPrecisionMultigrid:
         # each (phase, buffer-role state) is captured once into a CUDA graph and replayed afterwards.
         self.use_cuda_graphs = use_cuda_graphs
         self._graph_cache = None
+        # Helmholtz shift: solve (-lap + shift) u = f (implicit heat steps); 0 = the Poisson problem
+        if shift < 0:
+            raise ValueError("shift must be >= 0")
+        self.shift = float(shift)
         self.enable_precision_monitoring = False
         self.precision_switches: List[Dict[str, Any]] = []
         self._engine: Optional[CycleEngine] = None
@@ -126,7 +130,8 @@ class MixedPrecisionMultigrid:
             if c.nx < 5 or c.ny < 5:
                 break
             grids.append(c)
-        op = LaplacianOperator(-1.0)  # the convergent sign convention
+        # coefficient -1: the convergent sign convention
+        op = HelmholtzOperator(-1.0, self.shift) if self.shift else LaplacianOperator(-1.0)
         L = len(grids)
         self._engine = CycleEngine(
             grids, smoother=self._make_smoother(),
@@ -195,14 +200,15 @@ class MixedPrecisionMultigrid:
         if ops.vc_aligned(b64.u, b64.f, b64.tmp, b32.u, b32.f) and eng.kernels != "basic":
             if with_update:
                 ops.vc_defect_pass(b64.u, b64.tmp, b64.f, g.hx, g.hy, e_in=b32.u, r_out=b32.f, sumsq_out=ss,
-                                   loader=eng.loader)
+                                   loader=eng.loader, shift=self.shift)
                 b64.u, b64.tmp = b64.tmp, b64.u
             else:
-                ops.vc_defect_pass(b64.u, None, b64.f, g.hx, g.hy, r_out=b32.f, sumsq_out=ss, loader=eng.loader)
+                ops.vc_defect_pass(b64.u, None, b64.f, g.hx, g.hy, r_out=b32.f, sumsq_out=ss, loader=eng.loader,
+                                   shift=self.shift)
         else:  # strict basic kernels
             if with_update:
                 ops.axpy_(1.0, b32.u, b64.u)
-            ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp)
+            ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp, shift=self.shift)
             ss.copy_(ops.sumsq_async(b64.tmp, slot=1))
             ops.cast(b64.tmp, torch.float32, out=b32.f)
 
