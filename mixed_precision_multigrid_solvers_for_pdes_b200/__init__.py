@@ -7,6 +7,8 @@ from . import ops
 from ._lib import LIB_PATH, MGLibraryError
 from .core import Grid, PrecisionLevel, PrecisionManager
 from .applications.heat_solver import HeatSolver2D
+from .applications.poisson_solver import PoissonSolver2D
+from .preconditioning import MultigridPreconditioner
 from .operators import (BaseOperator, HelmholtzOperator, LaplacianOperator, ProlongationOperator,
                         RestrictionOperator)
 from .problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
@@ -17,7 +19,7 @@ from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, Ba
 __version__ = "0.1.0"
 GPU_AVAILABLE = True  # the only path there is
 
-__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "HeatSolver2D", "RestrictionOperator",
+__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "HeatSolver2D", "PoissonSolver2D", "MultigridPreconditioner", "RestrictionOperator",
            "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
            "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
            "SymmetricGaussSeidelSmoother", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",

@@ -150,6 +150,26 @@ class MultigridSolver(BaseSolver):
         out = like_input(u, was_np) if was_np else u.clone()
         return out, self.get_convergence_info()
 
+    def apply_cycles(self, rhs, num_cycles: int = 1, initial_guess=None):
+        """`num_cycles` cycles on A u = rhs from `initial_guess` (zero by default) with NO residual norms and no host
+        synchronisation: the preconditioner fast path (reference multigrid_preconditioner.py:119-163 uses
+        solve(tolerance=1e-16, max_iterations=num_cycles))."""
+        if not self.grids or self.engine is None or tuple(rhs.shape) != tuple(self.grids[0].shape):
+            raise ValueError("Multigrid not properly setup or grid mismatch")
+        eng = self.engine
+        f_in, was_np = to_device(rhs, device=eng.dev)
+        dts = [f_in.dtype] * len(self.grids)
+        b = eng.levels[0].bufs(f_in.dtype)
+        b.f.copy_(f_in)
+        if initial_guess is None:
+            b.u.zero_()
+        else:
+            b.u.copy_(to_device(initial_guess, device=eng.dev, dtype=f_in.dtype)[0])
+        for _ in range(num_cycles):
+            eng.cycle(dts, 0, None)
+        u = eng.levels[0].bufs(f_in.dtype).u
+        return like_input(u, True) if was_np else u.clone()
+
     def get_convergence_info(self) -> Dict[str, Any]:
         info = super().get_convergence_info()
         info.update({
