@@ -115,3 +115,18 @@ def test_cuda_graph_replay_is_bitwise_identical_to_eager(strategy):
     assert ie["residual_history"] == ig["residual_history"] == ig2["residual_history"]
     assert np.array_equal(ue, ug) and np.array_equal(ue, ug2)
     assert any(isinstance(v, tuple) for v in sg._graphs.values())
+
+
+@pytest.mark.parametrize("strategy", ["double", "adaptive"])
+def test_full_multigrid_start_saves_cycles(strategy):
+    n = 1025
+    p = PoissonProblem.manufactured(n, on_device=True)
+    u0, i0 = MixedPrecisionMultigrid(strategy).solve(p)
+    u1, i1 = MixedPrecisionMultigrid(strategy, fmg=True).solve(p)
+    assert i0["converged"] and i1["converged"] and i1["fmg"]
+    assert i1["iterations"] <= i0["iterations"] - 2, (i0["iterations"], i1["iterations"])
+    ref = O.mms_discretisation_error(n)
+    for u in (u0, u1):
+        assert abs(np.max(np.abs(u - O.mms_exact(n))) - ref) <= 0.01 * ref
+    # the FMG iterate alone is already at discretisation-error level: first residual far below the zero-start one
+    assert i1["residual_history"][0] < 0.05 * i0["residual_history"][0]
