@@ -167,6 +167,19 @@ MG_API int mg_coarse_solve_lexgs_h(void* u, const void* f, int nx, int ny, int64
                             double hx, double hy, double omega, double coefficient, double shift,
                             double tolerance, int max_iterations, double* info, int dtype, void* stream);
 
+/* Variable-coefficient operator A u = -div(a grad u) + shift*u with a nodal coefficient field `a` (same shape and
+ * dtype as u; arithmetic-mean face coefficients).  The reference advertises this problem class (README.md:175) but
+ * ships no operator for it: there is no reference arithmetic to mirror; a == 1, shift == 0 reduces to
+ * coefficient = -1 of the functions above.
+ * mg_varcoef_residual: r = f - A u (r = f on the boundary), or r = A u when apply_only != 0 (f may then be NULL).
+ * mg_varcoef_smooth_rbgs: in-place red-black Gauss-Seidel relaxing A u = f. */
+MG_API int mg_varcoef_residual(const void* u, const void* f, const void* a, void* r, int nx, int ny, int64_t ld_u,
+                        int64_t ld_f, int64_t ld_a, int64_t ld_r, double hx, double hy, double shift,
+                        int apply_only, int dtype, void* stream);
+MG_API int mg_varcoef_smooth_rbgs(void* u, const void* f, const void* a, int nx, int ny, int64_t ld_u,
+                           int64_t ld_f, int64_t ld_a, double hx, double hy, double shift, double omega,
+                           int sweeps, int dtype, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused, temporally blocked V/W-cycle passes ("vector path": TMA-staged, 16-byte aligned fields)
  *

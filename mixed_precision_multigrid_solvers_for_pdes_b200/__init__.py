@@ -10,7 +10,7 @@ from .applications.heat_solver import HeatSolver2D
 from .applications.poisson_solver import PoissonSolver2D
 from .preconditioning import MultigridPreconditioner
 from .operators import (BaseOperator, HelmholtzOperator, LaplacianOperator, ProlongationOperator,
-                        RestrictionOperator)
+                        RestrictionOperator, VariableCoefficientOperator, VariableCoefficientSmoother)
 from .problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
                        TimeSteppingMethod)
 from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
@@ -19,7 +19,7 @@ from .solvers import (MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, Ba
 __version__ = "0.1.0"
 GPU_AVAILABLE = True  # the only path there is
 
-__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "HeatSolver2D", "PoissonSolver2D", "MultigridPreconditioner", "RestrictionOperator",
+__all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "VariableCoefficientOperator", "VariableCoefficientSmoother", "HeatSolver2D", "PoissonSolver2D", "MultigridPreconditioner", "RestrictionOperator",
            "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
            "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
            "SymmetricGaussSeidelSmoother", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",

@@ -153,10 +153,10 @@ def test_c_oracle_solves_match_reference(solve_golden, golden_meta):
 
 
 def test_c_oracle_large_grid_matches_numpy_oracle():
-    n = 1025
+    n = 513
     f = O.mms_rhs(n)
-    a = O.OracleMultigrid(n, max_levels=9, max_iterations=2)
-    b = O.OracleMultigrid(n, max_levels=9, max_iterations=2, ops=CO)
+    a = O.OracleMultigrid(n, max_levels=8, max_iterations=2)
+    b = O.OracleMultigrid(n, max_levels=8, max_iterations=2, ops=CO)
     ua, ia = a.solve(f)
     ub, ib = b.solve(f)
     assert np.array_equal(ua, ub) and ia["residual_history"] == ib["residual_history"]
