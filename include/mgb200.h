@@ -260,6 +260,23 @@ MG_API int mg_vc_prolong_correct_smooth(const void* u_in, void* u_out, const voi
                                  int64_t ld_ci, double hx, double hy, double omega, int sweeps, int dtype,
                                  int flags, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The coarse end of a cycle in one launch: the complete V (cycle = 0), W (1) or F (2) sub-cycle of
+ * solvers/multigrid.py:253-337 over `nlev` levels starting at the (nx, ny) entry level, in place on u, by ONE
+ * thread block holding every level in shared memory (levels: red-black GS `pre`/`post` sweeps, residual + full
+ * weighting, bilinear prolongation + correction; coarsest level: lexicographic-GS solve to `coarse_tolerance`,
+ * solvers/base.py:258-285).  Levels 0..nlev-2 are `dtype`, the coarsest `coarse_dtype` (fp32 levels with an fp64
+ * coarsest level mirror the reference, which never converts the coarsest level, multigrid.py:270-272).
+ * Usable when mg_small_cycle_smem_bytes(...) <= 200 KiB (e.g. 129^2 fp32 or 65^2 fp64 entry levels);
+ * returns MG_ERR_UNSUPPORTED otherwise.  A W-cycle at 32769^2 visits the coarsest grid 8192 times: this
+ * kernel replaces ~12 launches per visit by one.  `info` (device, 2 doubles, may be NULL) = {sweeps, norm} of
+ * the last coarse solve; u_zero != 0: start from u = 0 without reading u. */
+MG_API int mg_small_cycle_smem_bytes(int nx, int ny, int nlev, int dtype, int coarse_dtype);
+MG_API int mg_small_cycle(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
+                   int nlev, int cycle, int pre, int post, double omega, double coefficient, double shift,
+                   double coarse_tolerance, int coarse_max_iterations, int u_zero, double* info, int dtype,
+                   int coarse_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

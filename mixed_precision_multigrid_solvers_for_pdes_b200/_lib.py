@@ -49,6 +49,8 @@ SIGNATURES = {
     "mg_residual_h": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _d, _i, _i, _p],
     "mg_smooth_rbgs_h": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _d, _i, _i, _p],
     "mg_coarse_solve_lexgs_h": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _d, _d, _d, _i, _p, _i, _p],
+    "mg_small_cycle_smem_bytes": [_i, _i, _i, _i, _i],
+    "mg_small_cycle": [_p, _p, _i, _i, _l, _l, _d, _d, _i, _i, _i, _i, _d, _d, _d, _d, _i, _i, _p, _i, _i, _p],
     "mg_vc_smooth": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _i, _i, _i, _p],
     "mg_vc_residual_restrict": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _i, _i, _p],
     "mg_vc_prolong_correct_smooth": [_p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _d, _d, _d, _i, _i, _i, _p],
@@ -56,7 +58,7 @@ SIGNATURES = {
 VC_PROLONG, VC_RESTRICT, VC_NORM, VC_LOADER_CPASYNC, VC_NO_STORE, VC_U_ZERO = 1, 2, 4, 16, 32, 64
 _RESTYPE = {"mg_status_string": C.c_char_p, "mg_launch_count": C.c_longlong}
 _NO_STATUS = {"mg_abi_version", "mg_launch_count", "mg_status_string", "mg_device_sm_count", "mg_sumsq_workspace_doubles",
-              "mg_vc_workspace_doubles"}
+              "mg_vc_workspace_doubles", "mg_small_cycle_smem_bytes"}
 
 _lib: Optional[C.CDLL] = None
 

@@ -38,7 +38,15 @@ template <typename T> struct StencilScalars {
   T shift;     // Helmholtz shift lambda >= 0: operator coeff*lap_h + lambda (0 for the reference's Poisson path)
   // reciprocal forms for the fast (vector/fused) kernels
   T ihx2, ihy2, inv_neg_diag;
+  // 1 when hx2, hy2 and neg_diag are exact powers of two: multiplying by the reciprocal then equals the
+  // reference's division bit for bit, and the strict kernels may skip the (slow, high-latency) fp64 divisions
+  int recip_exact;
 };
+
+inline bool is_pow2(double x) {
+  int e;
+  return x > 0 && frexp(x, &e) == 0.5;
+}
 
 template <typename T>
 inline StencilScalars<T> make_scalars(double hx, double hy, double omega, double coeff, double shift = 0.0) {
@@ -56,6 +64,7 @@ inline StencilScalars<T> make_scalars(double hx, double hy, double omega, double
   s.ihx2 = (T)1 / s.hx2;
   s.ihy2 = (T)1 / s.hy2;
   s.inv_neg_diag = (T)1 / s.neg_diag;
+  s.recip_exact = (is_pow2((double)s.hx2) && is_pow2((double)s.hy2) && is_pow2((double)s.neg_diag)) ? 1 : 0;
   return s;
 }
 
@@ -63,8 +72,14 @@ inline StencilScalars<T> make_scalars(double hx, double hy, double omega, double
 template <typename T>
 __device__ __forceinline__ T relax_strict(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
   using A = Strict<T>;
-  const T nb = A::add(A::div(A::add(up, dn), s.hx2), A::div(A::add(rt, lf), s.hy2));
-  const T unew = A::div(A::add(rhs, nb), s.neg_diag);
+  T unew;
+  if (s.recip_exact) {  // same bits as the divisions below (power-of-two scalings are exact)
+    const T nb = A::add(A::mul(A::add(up, dn), s.ihx2), A::mul(A::add(rt, lf), s.ihy2));
+    unew = A::mul(A::add(rhs, nb), s.inv_neg_diag);
+  } else {
+    const T nb = A::add(A::div(A::add(up, dn), s.hx2), A::div(A::add(rt, lf), s.hy2));
+    unew = A::div(A::add(rhs, nb), s.neg_diag);
+  }
   return A::add(A::mul(s.one_minus_omega, uc), A::mul(s.omega, unew));
 }
 
@@ -72,7 +87,9 @@ __device__ __forceinline__ T relax_strict(const StencilScalars<T>& s, T uc, T up
 template <typename T>
 __device__ __forceinline__ T apply_strict(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf) {
   using A = Strict<T>;
-  const T t = A::sub(A::add(A::div(A::add(up, dn), s.hx2), A::div(A::add(rt, lf), s.hy2)), A::mul(uc, s.cc));
+  const T t = s.recip_exact
+                  ? A::sub(A::add(A::mul(A::add(up, dn), s.ihx2), A::mul(A::add(rt, lf), s.ihy2)), A::mul(uc, s.cc))
+                  : A::sub(A::add(A::div(A::add(up, dn), s.hx2), A::div(A::add(rt, lf), s.hy2)), A::mul(uc, s.cc));
   const T au = A::mul(s.coeff, t);
   return s.shift != (T)0 ? A::add(au, A::mul(s.shift, uc)) : au;
 }

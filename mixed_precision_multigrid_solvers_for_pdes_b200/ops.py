@@ -310,3 +310,27 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
         ev1.record()
         TIMER.records.append((("update+" if e_in is not None else "") + ("resid32+N" if r_out is not None else "")
                               + f"/f64/{nx}x{ny}", ev0, ev1))
+
+
+SMALL_CYCLE_SMEM_LIMIT = 200 * 1024
+_CYCLES = {"V": 0, "W": 1, "F": 2}
+
+
+def small_cycle_fits(nx: int, ny: int, nlev: int, dtype, coarse_dtype) -> bool:
+    if nlev < 1 or nlev > 8:
+        return False
+    b = _lib.call("mg_small_cycle_smem_bytes", nx, ny, nlev, code(dtype), code(coarse_dtype))
+    return 0 < b <= SMALL_CYCLE_SMEM_LIMIT
+
+
+def small_cycle_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, *, nlev: int, cycle_type: str = "V",
+                 pre: int = 2, post: int = 2, omega: float = 1.0, coefficient: float = -1.0, shift: float = 0.0,
+                 coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000, coarse_dtype=None,
+                 u_zero: bool = False, info: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One complete sub-cycle over `nlev` levels in a single launch (mg_small_cycle), in place on u."""
+    nx, ny = u.shape
+    cd = coarse_dtype if coarse_dtype is not None else u.dtype
+    _lib.call("mg_small_cycle", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, nlev, _CYCLES[cycle_type],
+              pre, post, omega, coefficient, shift, coarse_tolerance, coarse_max_iterations, 1 if u_zero else 0,
+              info.data_ptr() if info is not None else None, code(u.dtype), code(cd), stream_ptr())
+    return u

@@ -50,7 +50,7 @@ class _Level:
 class CycleEngine:
     def __init__(self, grids: Sequence, *, smoother, coarse_solver, operators: Sequence, restriction_ops: Sequence,
                  prolongation_ops: Sequence, cycle_type: str = "V", pre: int = 2, post: int = 2,
-                 kernels: str = "auto", loader: str = "tma", device=None):
+                 kernels: str = "auto", loader: str = "tma", device=None, use_small_cycle: bool = True):
         self.dev = require_cuda(device)
         self.levels: List[_Level] = [_Level(g, self.dev) for g in grids]
         self.smoother, self.coarse_solver = smoother, coarse_solver
@@ -60,6 +60,8 @@ class CycleEngine:
             raise ValueError(f"kernels must be 'auto', 'basic' or 'fused', got {kernels!r}")
         self.kernels = kernels
         self.loader = loader
+        self.use_small_cycle = use_small_cycle
+        self._small_cache: Dict = {}
         self.coarse_info = torch.zeros(2, dtype=torch.float64, device=self.dev)
 
     # -- buffer roles (u / tmp swap on every out-of-place pass) ---------------------------------------
@@ -134,6 +136,40 @@ class CycleEngine:
                              "full_weighting restriction, bilinear prolongation and one dtype per level pair")
         return ok
 
+    # -- the coarse end of the hierarchy in one launch -------------------------------------------------------------
+    def _small_ok(self, lvl: int, level_dtypes: Sequence) -> bool:
+        """Can levels lvl..coarsest run as ONE mg_small_cycle launch (everything in shared memory)?"""
+        if self.kernels == "basic" or not self.use_small_cycle or self.cycle_type not in ("V", "W", "F"):
+            return False
+        L = self.num_levels
+        key = (lvl, tuple(str(torch_dtype(d)) for d in level_dtypes[lvl:]))
+        hit = self._small_cache.get(key)
+        if hit is not None:
+            return hit
+        ok = False
+        cs, sm = self.coarse_solver, self.smoother
+        dts = [torch_dtype(d) for d in level_dtypes[lvl:]]
+        if (getattr(sm, "kind", None) == "rbgs" and getattr(cs, "kind", None) == "lexgs" and getattr(cs, "omega", 1.0) == 1.0
+                and all(type(op).__name__ in _NATIVE_OPERATORS for op in self.operators[lvl:])
+                and all(getattr(r, "method", None) == "full_weighting" for r in self.restriction_ops[lvl:])
+                and all(getattr(p, "method", None) == "bilinear" for p in self.prolongation_ops[lvl:])
+                and len(set(dts[:-1])) <= 1 and (len(dts) == 1 or dts[-1] in (dts[0], torch.float64))
+                and len({(getattr(op, "coefficient", None), getattr(op, "shift", 0.0)) for op in self.operators[lvl:]}) == 1):
+            g = self.levels[lvl].grid
+            ok = ops.small_cycle_fits(g.nx, g.ny, L - lvl, dts[0], dts[-1])
+        self._small_cache[key] = ok
+        return ok
+
+    def _small_cycle(self, lvl: int, level_dtypes: Sequence, u_zero: bool) -> None:
+        g = self.levels[lvl].grid
+        b = self.levels[lvl].bufs(level_dtypes[lvl])
+        op, cs = self.operators[lvl], self.coarse_solver
+        ops.small_cycle_(b.u, b.f, g.hx, g.hy, nlev=self.num_levels - lvl, cycle_type=self.cycle_type, pre=self.pre,
+                         post=self.post, omega=self.smoother.omega, coefficient=op.coefficient,
+                         shift=getattr(op, "shift", 0.0), coarse_tolerance=cs.tolerance,
+                         coarse_max_iterations=cs.max_iterations, coarse_dtype=torch_dtype(level_dtypes[-1]),
+                         u_zero=u_zero, info=self.coarse_info)
+
     def _reps(self, lvl: int) -> int:
         L = self.num_levels
         if self.cycle_type == "V":
@@ -193,6 +229,9 @@ class CycleEngine:
         taken as zero whatever its buffer holds (the zero initial guess of a coarse error equation)."""
         L = self.num_levels
         b = self.levels[lvl].bufs(level_dtypes[lvl])
+        if precision_manager is None and self._small_ok(lvl, level_dtypes):
+            self._small_cycle(lvl, level_dtypes, u_zero)
+            return False
         if lvl == L - 1:
             if u_zero:
                 b.u.zero_()
