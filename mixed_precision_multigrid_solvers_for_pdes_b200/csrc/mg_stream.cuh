@@ -41,6 +41,15 @@ constexpr int STRIP = 128;    // columns per warp strip
 constexpr int BACK_NONE = 0, BACK_RESTRICT = 1, BACK_NORM = 2, BACK_RESID = 3;  // RESID: store fp32 residual + norm
 constexpr int FRONT_NONE = 0, FRONT_PROLONG = 1, FRONT_ADDFINE = 2;             // ADDFINE: u += (T)e, e fp32, fine grid
 constexpr int LOADER_TMA = 0, LOADER_CPASYNC = 1;
+// fp32 prolongation passes stage the coarse correction through the TMA ring too: RB/2 + 1 coarse rows of
+// COARSE_BOX_W columns per box of RB fine rows: 65 are needed, the box start is rounded down to a multiple of 4
+// columns (a TMA box must start 16-byte aligned in the inner dimension: an 8-byte aligned start raised "illegal
+// instruction" on sm_100a), so up to 67 + 1 = 68 columns = 272 bytes per row
+constexpr int COARSE_BOX_W = 68;
+// staged for fp32 always; for fp64 only when a BACK stage already limits the kernel to 2 blocks per SM by registers
+template <typename T, int FRONT, int BACK, int LOADER> struct StageCoarse {
+  static constexpr bool value = (FRONT == FRONT_PROLONG) && (LOADER == LOADER_TMA) && (sizeof(T) == 4 || BACK != BACK_NONE);
+};
 
 template <int NU, int BACK> struct Geometry {
   static constexpr int H = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // first owned local column (halo)
@@ -133,6 +142,14 @@ __device__ __forceinline__ void stg4(double* p, const double (&v)[4]) {
 }
 __device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+__device__ __forceinline__ void lds2(const float* p, float& a, float& b) {
+  const float2 t = *reinterpret_cast<const float2*>(p);
+  a = t.x; b = t.y;
+}
+__device__ __forceinline__ void lds2(const double* p, double& a, double& b) {
+  const double2 t = *reinterpret_cast<const double2*>(p);
+  a = t.x; b = t.y;
+}
 __device__ __forceinline__ void ldg2(const float* p, float& a, float& b) {
   const float2 t = __ldg(reinterpret_cast<const float2*>(p));
   a = t.x; b = t.y;
@@ -198,7 +215,13 @@ __global__ void __launch_bounds__(WARPS * 32)
   constexpr uint32_t ROW_BYTES = STRIP * sizeof(T);
   constexpr uint32_t BOX_BYTES = RB * ROW_BYTES;                            // one T array, one stage
   constexpr uint32_t EBOX_BYTES = FRONT == FRONT_ADDFINE ? RB * STRIP * 4 : 0;  // fp32 correction box
-  constexpr uint32_t STAGE_BYTES = 2 * BOX_BYTES + EBOX_BYTES;
+  // coarse rows of a prolongation pass: staged by TMA for fp32 (the __ldg path exposes ~6 long-scoreboard stalls per
+  // issue slot, ncu r01), read directly for fp64 / cp.async
+  constexpr bool STAGE_COARSE = StageCoarse<T, FRONT, BACK, LOADER>::value;
+  constexpr int CALIGN = 16 / (int)sizeof(T) - 1;  // box start rounded down to 16 bytes
+  constexpr uint32_t CBOX_TX = STAGE_COARSE ? (RB / 2 + 1) * COARSE_BOX_W * sizeof(T) : 0;  // bytes TMA delivers
+  constexpr uint32_t CBOX_BYTES = (CBOX_TX + 127u) & ~127u;                                     // ring slot (128-B aligned)
+  constexpr uint32_t STAGE_BYTES = 2 * BOX_BYTES + EBOX_BYTES + CBOX_BYTES;
 
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[WARPS][NSTAGE];
@@ -254,10 +277,13 @@ __global__ void __launch_bounds__(WARPS * 32)
     const int row0 = i_begin + box * RB;
     if (LOADER == LOADER_TMA) {
       if (lane == 0) {
-        mbar_expect_tx(&full_bar[warp][stage], (u_zero ? 0u : BOX_BYTES) + BOX_BYTES + EBOX_BYTES);
+        mbar_expect_tx(&full_bar[warp][stage], (u_zero ? 0u : BOX_BYTES) + BOX_BYTES + EBOX_BYTES + CBOX_TX);
         if (!u_zero) tma_load_2d(dst_u, &map_u, g0, row0, &full_bar[warp][stage]);
         tma_load_2d(dst_f, &map_f, g0, row0, &full_bar[warp][stage]);
         if (FRONT == FRONT_ADDFINE) tma_load_2d(dst_e, &map_e, g0, row0, &full_bar[warp][stage]);
+        // coarse rows row0/2 .. row0/2 + RB/2, coarse columns g0/2 .. (out-of-range parts arrive as zeros)
+        // (the box starts at a multiple of 4 columns = 16 bytes: sm_100a faulted on 8-byte aligned box starts)
+        if (STAGE_COARSE) tma_load_2d(dst_e, &map_e, (g0 >> 1) & ~CALIGN, row0 >> 1, &full_bar[warp][stage]);
       }
     } else {
       // per lane: its own 4 elements of every row of the box; zero-fill outside the domain
@@ -340,10 +366,16 @@ __global__ void __launch_bounds__(WARPS * 32)
     const T nxt = shfl_dn1(a);
     c[0] = a; c[1] = b; c[2] = (lane == 31) ? d : nxt;
   };
-  if (FRONT == FRONT_PROLONG) {
+  if (FRONT == FRONT_PROLONG && !STAGE_COARSE) {
     load_coarse_row(i_begin >> 1, c0, true);  // i_begin is even; >> floors for negatives
     load_coarse_row((i_begin >> 1) + 1, c1, true);
   }
+  // staged variant: row `rel` (0 .. RB/2) of the current box's coarse slab, columns 2*lane .. 2*lane + 2
+  auto read_coarse_row = [&](const T* sc_box, int rel, T(&c)[3]) {
+    const T* row = sc_box + rel * COARSE_BOX_W + ((g0 >> 1) & CALIGN) + 2 * lane;
+    lds2(row, c[0], c[1]);
+    c[2] = row[2];
+  };
 
   T* const uout = reinterpret_cast<T*>(p.u_out);
   T* const cout = reinterpret_cast<T*>(p.coarse_out);
@@ -353,6 +385,11 @@ __global__ void __launch_bounds__(WARPS * 32)
   //      touches is an interior point, so there are no boundary tests, selects or divergent branches. ----
   auto process_box = [&](auto masked_tag, const int ib, const T* su, const T* sf, const float* se) {
     constexpr bool MASKED = decltype(masked_tag)::value;
+    const T* sc_box = reinterpret_cast<const T*>(se - lane * LANE_V);  // coarse slab of this box (STAGE_COARSE)
+    if (STAGE_COARSE) {
+      read_coarse_row(sc_box, 0, c0);
+      read_coarse_row(sc_box, 1, c1);
+    }
     // rows stored by this box: ib - 2NU ... ib + RB - 1 - 2NU; all owned by the tile?  (uniform)
     const bool rows_owned = (ib - 2 * NU >= I0) && (ib + RB - 1 - 2 * NU < I1);
     T* orow = uout + (int64_t)(ib - 2 * NU) * p.ld_out + jbase;  // running output row pointer
@@ -408,7 +445,11 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (kpar == 1) {  // moving to the next coarse row pair
 #pragma unroll
           for (int e = 0; e < 3; ++e) c0[e] = c1[e];
-          load_coarse_row(((i + 1) >> 1) + 1, c1, MASKED);
+          if (STAGE_COARSE) {
+            if (k + 1 < RB) read_coarse_row(sc_box, (k + 1) / 2 + 1, c1);  // the next box reloads both rows
+          } else {
+            load_coarse_row(((i + 1) >> 1) + 1, c1, MASKED);
+          }
         }
       }
 

@@ -23,13 +23,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // (nx, ny) row-major field with pitch ld  ->  2-D tiled map, box = RB rows x 128 columns, zero OOB fill
-static int make_map(CUtensorMap* m, const void* base, int nx, int ny, int64_t ld, int dtype) {
+static int make_map(CUtensorMap* m, const void* base, int nx, int ny, int64_t ld, int dtype, int box_w = STRIP,
+                    int box_h = RB) {
   auto enc = get_encode();
   if (!enc) return MG_ERR_UNSUPPORTED;
   const size_t esz = dtype == MG_F64 ? 8 : 4;
   cuuint64_t dims[2] = {(cuuint64_t)ny, (cuuint64_t)nx};
   cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {(cuuint32_t)STRIP, (cuuint32_t)RB};
+  cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, dtype == MG_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -136,6 +137,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
     if (!u_zero) rc = make_map(&m.u, u_in, nx, ny, ld_in, dtype);
     if (rc == MG_OK) rc = make_map(&m.f, f, nx, ny, ld_f, dtype);
     if (rc == MG_OK && front == FRONT_ADDFINE) rc = make_map(&m.e, fine_in, nx, ny, ld_fi, MG_F32);
+    if (rc == MG_OK && front == FRONT_PROLONG)  // the coarse correction rides the TMA ring (see StageCoarse)
+      rc = make_map(&m.e, coarse_in, nxc, nyc, ld_ci, dtype, COARSE_BOX_W, RB / 2 + 1);
     if (rc != MG_OK) return rc;
   }
   cudaStream_t st = as_stream(stream);

@@ -19,9 +19,12 @@ struct Maps {
 
 template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE>
 static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
-  constexpr int NS = Stages<T>::N;
+  // fp32 prolongation passes carry the coarse slab in every stage: 2 stages keep 5 blocks (20 warps) per SM
+  constexpr int NS = (sizeof(T) == 4 && FRONT == FRONT_PROLONG && LOADER == LOADER_TMA) ? 2 : Stages<T>::N;
   auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, WARPS, NS, RB>;
-  constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0);
+  constexpr bool stage_coarse = StageCoarse<T, FRONT, BACK, LOADER>::value;
+  constexpr size_t cbox = stage_coarse ? ((((size_t)(RB / 2 + 1) * COARSE_BOX_W * sizeof(T)) + 127) & ~(size_t)127) : 0;
+  constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0) + cbox;
   constexpr size_t smem = (size_t)WARPS * NS * stage_bytes;
   static bool configured[64] = {false};
   int dev = 0;
