@@ -275,7 +275,12 @@ def gpu_arm(a):
             step()
         e1.record()
         torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+        ms = e0.elapsed_time(e1)
+        # keep the GPU under the same load until the sampler (200 ms period) has seen it for >= 1.5 s; untimed
+        t_end = time.perf_counter() + max(0.0, 1.5 - ms * 1e-3)
+        while time.perf_counter() < t_end:
+            step()
+        torch.cuda.synchronize()
     replayed = solver._graph_cache.captured
     # kernels launched per step: counted by the library on an eager pass of the same steps below
     value = n * n * a.steps / (ms * 1e-3)
