@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=4097, help="grid of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
+    ap.add_argument("--strong", action="store_true",
+                    help="multi-GPU: --n is the GLOBAL grid (n x n on the unit square) split into row slabs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()

@@ -564,8 +564,12 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
 
     from . import _lib, ops
     n = a.n
-    nx, ny = world * (n - 1) + 1, n
-    domain = (0.0, float(world), 0.0, 1.0)  # square cells, h = 1/(n-1): same spacing as the 1-GPU workload
+    strong = bool(getattr(a, "strong", False))
+    if strong:  # BASELINE configs[3] style: one n x n grid on the unit square split over the GPUs
+        nx, ny, domain = n, n, (0.0, 1.0, 0.0, 1.0)
+    else:
+        nx, ny = world * (n - 1) + 1, n
+        domain = (0.0, float(world), 0.0, 1.0)  # square cells, h = 1/(n-1): same spacing as the 1-GPU workload
     tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
@@ -610,7 +614,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     value = nx * ny * a.steps / (ms * 1e-3)
     # per-kernel durations and launch counts: the same steps once more, eagerly, with events on rank 0
     sol.graphs.enabled = False
-    ops.TIMER = ops.KernelTimer(min_points=(n - 1) * n // 2) if rank == 0 else None
+    ops.TIMER = ops.KernelTimer(min_points=sol.s0.loc_nx * ny // 2) if rank == 0 else None
     launches0 = _lib.call("mg_launch_count")
     ex0 = sol.eng.exchanges
     for _ in range(a.steps):
@@ -672,10 +676,11 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     clocks = clk.summary()
     return {
         "metric": _metric_name(), "value": value, "unit": "unknowns/s", "n_gpus": world, "steps": a.steps,
-        "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, a.warmup), "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f32 cycle / f64 iterate+residual" if sol.mode in ("switch", "refine") else sol.mode,
         "data": "synthetic",
-        "config": {"workload": f"2D Poisson {nx}x{ny} ({n - 1} rows per GPU) manufactured sin*sin on (0,{world})x(0,1), "
+        "config": {"workload": f"2D Poisson {nx}x{ny} ({(nx - 1) // world} rows per GPU) manufactured sin*sin on "
+                               f"({domain[0]:g},{domain[1]:g})x(0,1), "
                                f"{a.cycle}(2,2) red-black GS, precision_strategy={a.strategy}, row slabs over {world} GPUs",
                    "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": GHOST,
                    "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
