@@ -45,7 +45,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=16385, help="fine grid points per side (per GPU slab height for N>1)")
+    ap.add_argument("--n", "--size", dest="n", type=int, default=16385,
+                    help="fine grid points per side (per GPU slab height for N>1); use --size under torchrun, whose "
+                         "own parser rejects --n as an ambiguous abbreviation")
     ap.add_argument("--strategy", default="adaptive")
     ap.add_argument("--cycle", default="V")
     ap.add_argument("--loader", default="tma")
