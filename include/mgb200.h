@@ -186,6 +186,7 @@ MG_API int mg_varcoef_smooth_rbgs(void* u, const void* f, const void* a, int nx,
  * One launch performs, in one pass over HBM and out of place (u_in -> u_out, u_out != u_in):
  *     [MG_VC_PROLONG: u += bilinear P(coarse_in)]                 (transfer.py:234-267, multigrid.py:329)
  *     -> `sweeps` (0..2) red-black Gauss-Seidel sweeps            (smoothers.py:175-207)
+ *        or, with MG_VC_JACOBI, damped-Jacobi sweeps              (smoothers.py:41-86)
  *     -> [MG_VC_RESTRICT: coarse_out = full-weighting R(f - A u)] (laplacian.py:105-124, transfer.py:100-124)
  *        or [MG_VC_NORM: sumsq_out[0] = sum over all points of (f - A u)^2]  (grid.py:174-187)
  * so a V(2,2) level costs three passes: smooth+residual+restrict going down, prolong+correct+smooth
@@ -200,6 +201,10 @@ MG_API int mg_varcoef_smooth_rbgs(void* u, const void* f, const void* a, int nx,
 #define MG_VC_NO_STORE 32        /* do not write u_out (pure residual passes, sweeps = 0) */
 #define MG_VC_U_ZERO 64          /* u_in is identically zero and is not read (u_in may be NULL): the first
                                     pre-smoothing pass of every coarse-level / error-equation solve */
+#define MG_VC_JACOBI 128         /* the `sweeps` are damped-Jacobi sweeps (JacobiSmoother / WeightedJacobiSmoother,
+                                    smoothers.py:41-86, 210-225; omega = relaxation parameter) instead of red-black
+                                    GS: one pipeline stage per sweep, previous-iterate rows kept in registers.
+                                    TMA loader only (MG_ERR_UNSUPPORTED together with MG_VC_LOADER_CPASYNC) */
 #define MG_VC_ROWS(r) (((r) & 0xFFF) << 8) /* override rows per tile (0 = auto) */
 
 /* doubles of workspace MG_VC_NORM needs for an (nx, ny) field */

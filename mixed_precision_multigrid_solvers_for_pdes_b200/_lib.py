@@ -55,7 +55,7 @@ SIGNATURES = {
     "mg_vc_residual_restrict": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _i, _i, _p],
     "mg_vc_prolong_correct_smooth": [_p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _d, _d, _d, _i, _i, _i, _p],
 }
-VC_PROLONG, VC_RESTRICT, VC_NORM, VC_LOADER_CPASYNC, VC_NO_STORE, VC_U_ZERO = 1, 2, 4, 16, 32, 64
+VC_PROLONG, VC_RESTRICT, VC_NORM, VC_LOADER_CPASYNC, VC_NO_STORE, VC_U_ZERO, VC_JACOBI = 1, 2, 4, 16, 32, 64, 128
 _RESTYPE = {"mg_status_string": C.c_char_p, "mg_launch_count": C.c_longlong}
 _NO_STATUS = {"mg_abi_version", "mg_launch_count", "mg_status_string", "mg_device_sm_count", "mg_sumsq_workspace_doubles",
               "mg_vc_workspace_doubles", "mg_small_cycle_smem_bytes"}

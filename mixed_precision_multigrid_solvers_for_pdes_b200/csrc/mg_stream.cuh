@@ -3,7 +3,7 @@
 // One kernel template covers the three fused passes of a V/W-cycle level:
 //
 //   [FRONT: u += P e_c]  ->  NU x (red half-sweep, black half-sweep)  ->  [BACK: r = f - A u, then
-//                                                          full-weighting restriction  OR  sum r^2]
+//                            or NU damped-Jacobi sweeps            full-weighting restriction  OR  sum r^2]
 //
 // in ONE pass over HBM: u_in and f are read once, u_out written once (plus 1/4-size coarse
 // traffic).  Out of place (u_in -> u_out), so tiles never race on halos.
@@ -51,15 +51,20 @@ template <typename T, int FRONT, int BACK, int LOADER> struct StageCoarse {
   static constexpr bool value = (FRONT == FRONT_PROLONG) && (LOADER == LOADER_TMA) && (sizeof(T) == 4 || BACK != BACK_NONE);
 };
 
-template <int NU, int BACK> struct Geometry {
-  static constexpr int H = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // first owned local column (halo)
+constexpr int SMOOTH_RBGS = 0, SMOOTH_JACOBI = 1;
+// pipeline stages of `nu` sweeps: a red-black sweep is two half-sweep stages, a Jacobi sweep is one
+constexpr int num_stages(int smooth, int nu) { return smooth == SMOOTH_JACOBI ? nu : 2 * nu; }
+
+// NS = number of pipeline stages; every stage widens the dependency cone by one row / column
+template <int NS, int BACK> struct Geometry {
+  static constexpr int H = ((NS + (BACK != BACK_NONE ? 2 : 0)) + 1) & ~1;  // halo, rounded up to even
   static constexpr int OWN_LO = H < 4 ? 4 : H;                    // local column 4 is global column g0+4
   static constexpr int OWN_HI = STRIP - 1 - OWN_LO;
   static constexpr int STRIDE = OWN_HI - OWN_LO + 1;              // multiple of 4
-  static constexpr int ROW_LEAD = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // rows streamed before the first owned row
-  static constexpr int ROW_TAIL = 2 * NU + (BACK != BACK_NONE ? 2 : 0);  // rows streamed after the last owned row
-  static constexpr int WR = 2 * NU + 2 + (BACK != BACK_NONE ? 1 : 0);    // u window (ages 0..WR-1)
-  static constexpr int FR = 2 * NU + 1 + (BACK != BACK_NONE ? 1 : 0);    // f window (ages 0..FR-1)
+  static constexpr int ROW_LEAD = H;  // rows streamed before the first owned row (even: row parity, coarse mapping)
+  static constexpr int ROW_TAIL = H;  // rows streamed after the last owned row
+  static constexpr int WR = NS + 2 + (BACK != BACK_NONE ? 1 : 0);    // u window (ages 0..WR-1)
+  static constexpr int FR = NS + 1 + (BACK != BACK_NONE ? 1 : 0);    // f window (ages 0..FR-1)
 };
 
 struct PassParams {
@@ -192,6 +197,16 @@ __device__ __forceinline__ T relax_sel(const StencilScalars<T>& s, T uc, T up, T
   if (SIMPLE) return relax_iso1<T>(s, up, dn, rt, lf, rhs);
   return relax_fast<T>(s, uc, up, dn, rt, lf, rhs);
 }
+// Damped Jacobi point update: the relaxation blend (1-omega)*u_old + omega*u_new keeps the reference's two rounded
+// products and rounded sum (smoothers.py:82; no FMA contraction), so with power-of-two spacings the result is
+// bit-identical to the strict kernel for any omega.  omega == 1 (SIMPLE) makes the blend the identity.
+template <bool SIMPLE, typename T>
+__device__ __forceinline__ T relax_jacobi(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
+  if (SIMPLE) return relax_iso1<T>(s, up, dn, rt, lf, rhs);
+  const T nb = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
+  const T unew = (rhs + nb) * s.inv_neg_diag;
+  return Strict<T>::add(Strict<T>::mul(s.one_minus_omega, uc), Strict<T>::mul(s.omega, unew));
+}
 template <bool SIMPLE, typename T>
 __device__ __forceinline__ T residual_sel(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
   if (SIMPLE) return residual_iso<T>(s, uc, up, dn, rt, lf, f);
@@ -201,11 +216,12 @@ __device__ __forceinline__ T residual_sel(const StencilScalars<T>& s, T uc, T up
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int WARPS, int NSTAGE, int RB>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH, int WARPS, int NSTAGE, int RB>
 __global__ void __launch_bounds__(WARPS * 32)
     rbgs_stream_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_f,
                        const __grid_constant__ CUtensorMap map_e, const PassParams p, const StencilScalars<T> sc) {
-  using G = Geometry<NU, BACK>;
+  constexpr int NS = num_stages(SMOOTH, NU);  // pipeline stages; the row loaded NS steps ago is final
+  using G = Geometry<NS, BACK>;
   static_assert(RB % 2 == 0, "row parity must be static inside a box");
   static_assert(FRONT != FRONT_ADDFINE || sizeof(T) == 8, "ADDFINE adds an fp32 correction to an fp64 iterate");
   static_assert(BACK != BACK_RESID || sizeof(T) == 8, "RESID rounds an fp64 residual to fp32");
@@ -338,6 +354,13 @@ __global__ void __launch_bounds__(WARPS * 32)
   for (int a = 0; a < FR; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) fr[a][e] = (T)0;
+  // Jacobi: stage s also needs the PREVIOUS iterate of the older neighbour row, which stage s itself overwrote one
+  // step earlier; pj[s] keeps that row (version s-1 of the row of age s+1)
+  T pj[NS + 1][4];
+#pragma unroll
+  for (int a = 0; a <= NS; ++a)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pj[a][e] = (T)0;
   T rr[3][4];  // residual rows (BACK_RESTRICT): rr[0] newest
 #pragma unroll
   for (int a = 0; a < 3; ++a)
@@ -390,9 +413,9 @@ __global__ void __launch_bounds__(WARPS * 32)
       read_coarse_row(sc_box, 0, c0);
       read_coarse_row(sc_box, 1, c1);
     }
-    // rows stored by this box: ib - 2NU ... ib + RB - 1 - 2NU; all owned by the tile?  (uniform)
-    const bool rows_owned = (ib - 2 * NU >= I0) && (ib + RB - 1 - 2 * NU < I1);
-    T* orow = uout + (int64_t)(ib - 2 * NU) * p.ld_out + jbase;  // running output row pointer
+    // rows stored by this box: ib - NS ... ib + RB - 1 - NS; all owned by the tile?  (uniform)
+    const bool rows_owned = (ib - NS >= I0) && (ib + RB - 1 - NS < I1);
+    T* orow = uout + (int64_t)(ib - NS) * p.ld_out + jbase;  // running output row pointer
 #pragma unroll
     for (int k = 0; k < RB; ++k) {
       const int i = ib + k;  // newest row; parity of i == parity of k
@@ -453,11 +476,31 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
       }
 
-      // (2) the 2*NU half-sweeps, stage s on the row of age s
+      // (2) the NS stages, stage s on the row of age s
 #pragma unroll
-      for (int s = 1; s <= 2 * NU; ++s) {
+      for (int s = 1; s <= NS; ++s) {
         const int q = i - s;
-        if (!MASKED || (q >= 1 && q <= nx - 2)) {  // warp-uniform
+        if (SMOOTH == SMOOTH_JACOBI) {
+          // damped Jacobi (smoothers.py:41-86): every point from the previous iterate; the newer neighbour row (age
+          // s-1) was brought to iterate s-1 by stage s-1 in this step, the older one is kept in pj[s]
+          T old[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) old[e] = w[s][e];
+          if (!MASKED || (q >= 1 && q <= nx - 2)) {  // warp-uniform
+            const T lfx = shfl_up1(old[3]);
+            const T rtx = shfl_dn1(old[0]);
+            const T n0 = relax_jacobi<SIMPLE, T>(sc, old[0], w[s - 1][0], pj[s][0], old[1], lfx, fr[s][0]);
+            const T n1 = relax_jacobi<SIMPLE, T>(sc, old[1], w[s - 1][1], pj[s][1], old[2], old[0], fr[s][1]);
+            const T n2 = relax_jacobi<SIMPLE, T>(sc, old[2], w[s - 1][2], pj[s][2], old[3], old[1], fr[s][2]);
+            const T n3 = relax_jacobi<SIMPLE, T>(sc, old[3], w[s - 1][3], pj[s][3], rtx, old[2], fr[s][3]);
+            w[s][0] = (!MASKED || (upd & 1u)) ? n0 : old[0];
+            w[s][1] = (!MASKED || (upd & 2u)) ? n1 : old[1];
+            w[s][2] = (!MASKED || (upd & 4u)) ? n2 : old[2];
+            w[s][3] = (!MASKED || (upd & 8u)) ? n3 : old[3];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) pj[s][e] = old[e];
+        } else if (!MASKED || (q >= 1 && q <= nx - 2)) {  // warp-uniform
           // colour of stage s is (s-1)&1 (red = (row+col) even first); col parity == element parity
           const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element, compile-time after unrolling
           if (e0 == 0) {
@@ -476,30 +519,30 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
       }
 
-      // (3) the row of age 2NU is final: store the owned part (predicated stores, no divergent branch)
+      // (3) the row of age NS is final: store the owned part (predicated stores, no divergent branch)
       {
-        const int qf = i - 2 * NU;
+        const int qf = i - NS;
         const bool row_ok = store_u && (rows_owned || (qf >= I0 && qf < I1));
         T* dst = orow;
         orow += p.ld_out;
         if (!MASKED) {  // interior strip: ownership changes only at even columns
-          if (row_ok && own == 0xFu) stg4(dst, w[2 * NU]);
-          if (row_ok && own == 0x3u) stg2(dst, w[2 * NU][0], w[2 * NU][1]);
-          if (row_ok && own == 0xCu) stg2(dst + 2, w[2 * NU][2], w[2 * NU][3]);
+          if (row_ok && own == 0xFu) stg4(dst, w[NS]);
+          if (row_ok && own == 0x3u) stg2(dst, w[NS][0], w[NS][1]);
+          if (row_ok && own == 0xCu) stg2(dst + 2, w[NS][2], w[NS][3]);
         } else if (row_ok && own != 0u) {
           if (own == 0xFu) {
-            stg4(dst, w[2 * NU]);
+            stg4(dst, w[NS]);
           } else {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if ((own >> e) & 1u) dst[e] = w[2 * NU][e];
+              if ((own >> e) & 1u) dst[e] = w[NS][e];
           }
         }
       }
 
-      // (4) BACK: residual of the row of age 2NU+1 (its neighbours are final)
+      // (4) BACK: residual of the row of age NS+1 (its neighbours are final)
       if (HAS_BACK) {
-        constexpr int A = 2 * NU + 1;
+        constexpr int A = NS + 1;
         const int q2 = i - A;
         T r[4] = {(T)0, (T)0, (T)0, (T)0};
         if (!MASKED || (q2 >= 0 && q2 < nx)) {
@@ -551,7 +594,7 @@ __global__ void __launch_bounds__(WARPS * 32)
             rr[1][e] = rr[0][e];
             rr[0][e] = r[e];
           }
-          if (kpar == 0) {  // q2 = i - 2NU - 1 is odd: rows q2-2, q2-1 (centre, even), q2 are complete
+          if (kpar == (NS & 1)) {  // q2 = i - NS - 1 is odd: rows q2-2, q2-1 (centre, even), q2 are complete
             const int fi = q2 - 1;  // fine centre row
             const int ic = fi >> 1;
             if (fi >= I0 && fi < I1) {  // owned coarse row (warp-uniform); I0 >= 0, I1 <= nx
@@ -601,10 +644,10 @@ __global__ void __launch_bounds__(WARPS * 32)
     const T* sf = su + RB * STRIP;
     const float* se = reinterpret_cast<const float*>(ring + (size_t)stage * STAGE_BYTES + 2 * BOX_BYTES) + lane * LANE_V;
     const int ib = i_begin + box * RB;
-    // interior fast path: every row evaluated in this box (oldest: ib - 2NU - 1 with a BACK stage) and the
+    // interior fast path: every row evaluated in this box (oldest: ib - NS - 1 with a BACK stage) and the
     // newest row ib + RB - 1 are interior rows, and the strip has no boundary column
     // (with restriction also the centre row q2 - 1 of the oldest coarse row, hence 3 instead of 1)
-    constexpr int OLDEST = 2 * NU + (BACK == BACK_RESTRICT ? 3 : (HAS_BACK ? 1 : 0));
+    constexpr int OLDEST = NS + (BACK == BACK_RESTRICT ? 3 : (HAS_BACK ? 1 : 0));
     const bool fast = strip_interior && (ib - OLDEST >= 1) && (ib + RB - 1 <= nx - 2);
     if (fast) process_box(FalseTag{}, ib, su, sf, se);
     else process_box(TrueTag{}, ib, su, sf, se);

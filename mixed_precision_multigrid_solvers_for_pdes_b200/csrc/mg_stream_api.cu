@@ -5,10 +5,10 @@
 
 namespace mg {
 namespace stream {
-int launch_pass_f32_tma(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f32_cpa(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f64_tma(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
-int launch_pass_f64_cpa(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f32_tma(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f32_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_tma(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f64_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -38,13 +38,10 @@ static int make_map(CUtensorMap* m, const void* base, int nx, int ny, int64_t ld
   return r == CUDA_SUCCESS ? MG_OK : MG_ERR_BADARG;
 }
 
-static inline int strip_stride(int nu, int back) {
-  const int h = 2 * nu + (back ? 2 : 0);
-  const int lo = h < 4 ? 4 : h;
-  return STRIP - 2 * lo;
-}
-static inline int num_strips(int ny, int nu, int back) {
-  const int h = 2 * nu + (back ? 2 : 0);
+// halo of a pass with `ns` pipeline stages (Geometry<NS, BACK>::H)
+static inline int halo(int ns, int back) { return ((ns + (back ? 2 : 0)) + 1) & ~1; }
+static inline int num_strips(int ny, int ns, int back) {
+  const int h = halo(ns, back);
   const int lo = h < 4 ? 4 : h, hi = STRIP - 1 - lo, stride = hi - lo + 1;
   // strip k owns global columns up to stride*k - 4 + hi
   int k = 0;
@@ -84,11 +81,14 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
   const bool store = (flags & MG_VC_NO_STORE) == 0;
   const bool u_zero = (flags & MG_VC_U_ZERO) != 0;
+  const int smooth = (flags & MG_VC_JACOBI) ? SMOOTH_JACOBI : SMOOTH_RBGS;
+  const int ns = num_stages(smooth, sweeps);  // pipeline stages of the smoothing part
   const int rows_override = (flags >> 8) & 0xFFF;
   if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
   if (!f || nx < 3 || ny < 3 || ld_f < ny || hx <= 0 || hy <= 0 || !(shift >= 0.0)) return MG_ERR_BADARG;
   if (!u_zero && (!u_in || ld_in < ny)) return MG_ERR_BADARG;
   if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
+  if (smooth == SMOOTH_JACOBI && cpa && sweeps > 0) return MG_ERR_UNSUPPORTED;  // Jacobi passes are TMA-staged only
   if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
   if (!store && back == BACK_NONE) return MG_ERR_BADARG;
   if (sweeps == 0 && front == FRONT_NONE && back == BACK_NONE) return MG_ERR_BADARG;
@@ -126,8 +126,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   p.u_zero = u_zero ? 1 : 0;
   p.norm_row_lo = norm_lo < 0 ? 0 : norm_lo;
   p.norm_row_hi = (norm_hi < 0 || norm_hi > nx) ? nx : norm_hi;
-  p.nstrips = num_strips(ny, sweeps, back);
-  p.rows_per_tile = pick_rows(nx, p.nstrips, 4 * sweeps + (back ? 4 : 0) + 2, rows_override);
+  p.nstrips = num_strips(ny, ns, back);
+  p.rows_per_tile = pick_rows(nx, p.nstrips, 2 * halo(ns, back) + 2, rows_override);
   p.store_u = store ? 1 : 0;
 
   Maps m;
@@ -146,12 +146,12 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   int rc;
   if (dtype == MG_F64) {
     auto sc = make_scalars<double>(hx, hy, omega, coefficient, shift);
-    rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, simple, m, p, sc, st)
-             : launch_pass_f64_tma(sweeps, front, back, simple, m, p, sc, st);
+    rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, simple, smooth, m, p, sc, st)
+             : launch_pass_f64_tma(sweeps, front, back, simple, smooth, m, p, sc, st);
   } else {
     auto sc = make_scalars<float>(hx, hy, omega, coefficient, shift);
-    rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, simple, m, p, sc, st)
-             : launch_pass_f32_tma(sweeps, front, back, simple, m, p, sc, st);
+    rc = cpa ? launch_pass_f32_cpa(sweeps, front, back, simple, smooth, m, p, sc, st)
+             : launch_pass_f32_tma(sweeps, front, back, simple, smooth, m, p, sc, st);
   }
   if (rc != MG_OK) return rc;
   if (norm) {
@@ -166,7 +166,7 @@ extern "C" {
 
 int mg_vc_workspace_doubles(int nx, int ny) {
   if (nx < 3 || ny < 3) return 0;
-  const int nstrips = num_strips(ny, 0, 1) + WARPS;  // smallest stride => most strips
+  const int nstrips = num_strips(ny, 4, 1) + WARPS;  // widest halo => smallest stride => most strips
   const int ntiles = (nx + 7) / 8;
   return nstrips * ntiles + 8;
 }

@@ -17,11 +17,11 @@ struct Maps {
   CUtensorMap u, f, e;
 };
 
-template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH = SMOOTH_RBGS>
 static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
   // fp32 prolongation passes carry the coarse slab in every stage: 2 stages keep 5 blocks (20 warps) per SM
   constexpr int NS = (sizeof(T) == 4 && FRONT == FRONT_PROLONG && LOADER == LOADER_TMA) ? 2 : Stages<T>::N;
-  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, WARPS, NS, RB>;
+  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, SMOOTH, WARPS, NS, RB>;
   constexpr bool stage_coarse = StageCoarse<T, FRONT, BACK, LOADER>::value;
   constexpr size_t cbox = stage_coarse ? ((((size_t)(RB / 2 + 1) * COARSE_BOX_W * sizeof(T)) + 127) & ~(size_t)127) : 0;
   constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0) + cbox;
@@ -39,9 +39,23 @@ static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T
   return 0;
 }
 
+// smooth: SMOOTH_RBGS or SMOOTH_JACOBI (damped Jacobi sweeps; TMA loader only, and always the general point
+// update: omega = 1 Jacobi is not a smoother, so it gets no specialised instantiation)
 template <typename T, int LOADER>
-int launch_pass(int nu, int front, int back, bool simple, const Maps& m, const PassParams& p,
+int launch_pass(int nu, int front, int back, bool simple, int smooth, const Maps& m, const PassParams& p,
                 const StencilScalars<T>& sc, cudaStream_t st) {
+  if (smooth == SMOOTH_JACOBI && nu > 0) {
+    if constexpr (LOADER == LOADER_TMA) {
+#define MG_JCASE(NU_, FR_, BK_) \
+  if (nu == NU_ && front == FR_ && back == BK_) return launch_one<T, NU_, FR_, BK_, LOADER, false, SMOOTH_JACOBI>(m, p, sc, st);
+      MG_JCASE(1, FRONT_NONE, BACK_NONE) MG_JCASE(1, FRONT_NONE, BACK_RESTRICT) MG_JCASE(1, FRONT_NONE, BACK_NORM)
+      MG_JCASE(1, FRONT_PROLONG, BACK_NONE) MG_JCASE(1, FRONT_PROLONG, BACK_RESTRICT) MG_JCASE(1, FRONT_PROLONG, BACK_NORM)
+      MG_JCASE(2, FRONT_NONE, BACK_NONE) MG_JCASE(2, FRONT_NONE, BACK_RESTRICT) MG_JCASE(2, FRONT_NONE, BACK_NORM)
+      MG_JCASE(2, FRONT_PROLONG, BACK_NONE) MG_JCASE(2, FRONT_PROLONG, BACK_RESTRICT) MG_JCASE(2, FRONT_PROLONG, BACK_NORM)
+#undef MG_JCASE
+    }
+    return MG_ERR_UNSUPPORTED;
+  }
 #define MG_CASE(NU_, FR_, BK_)                                                           \
   if (nu == NU_ && front == FR_ && back == BK_)                                          \
     return simple ? launch_one<T, NU_, FR_, BK_, LOADER, true>(m, p, sc, st)             \

@@ -149,9 +149,17 @@ class DeviceBackend:
     def vc_defect_pass(self, *a, **k):
         return self.ops.vc_defect_pass(*a, loader=self.loader, **k)
 
-    def make_coarse_engine(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max):
+    def sumsq(self, t) -> torch.Tensor:
+        """Sum of squares of a (row window of a) pitched field as a 1-element device tensor (no sync)."""
+        return self.ops.sumsq_async(t, slot=2).clone()
+
+    def apply_laplacian(self, u, hx, hy):
+        """lap_h(u) on the interior of the local array, 0 on its first/last rows and columns."""
+        return self.ops.apply_laplacian(u, hx, hy, 1.0)
+
+    def make_coarse_engine(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0):
         from .core.grid import Grid
-        from .operators.laplacian import LaplacianOperator
+        from .operators.laplacian import HelmholtzOperator, LaplacianOperator
         from .operators.transfer import ProlongationOperator, RestrictionOperator
         from .solvers.engine import CycleEngine
         from .solvers.smoothers import GaussSeidelSmoother
@@ -159,7 +167,7 @@ class DeviceBackend:
         for _ in range(1, levels):
             grids.append(grids[-1].coarsen())
         L = len(grids)
-        op = LaplacianOperator(-1.0)
+        op = HelmholtzOperator(-1.0, shift) if shift else LaplacianOperator(-1.0)
         eng = CycleEngine(grids, smoother=GaussSeidelSmoother(red_black=True),
                           coarse_solver=GaussSeidelSmoother(max_iterations=coarse_max, tolerance=coarse_tol),
                           operators=[op] * L, restriction_ops=[RestrictionOperator()] * max(0, L - 1),
@@ -196,9 +204,12 @@ class DistributedCycleEngine:
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), num_levels: Optional[int] = None,
                  cycle_type: str = "V", pre: int = 2, post: int = 2, agglomerate_below: int = 1025,
                  dist_levels: Optional[int] = None, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
-                 backend=None, group=None, device=None):
+                 shift: float = 0.0, backend=None, group=None, device=None):
         if not (1 <= pre <= 2 and 1 <= post <= 2):
             raise ValueError("the distributed engine runs 1 or 2 pre/post sweeps per pass")
+        if not shift >= 0.0:
+            raise ValueError("shift must be >= 0")
+        self.shift = float(shift)  # Helmholtz term of the operator -lap_h + shift (0: Poisson); same on every level
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -220,7 +231,9 @@ class DistributedCycleEngine:
         self.valid: Dict[int, int] = {}  # data_ptr -> number of ghost rows per side that currently hold exact values
         an, am = self.part.agg_shape
         self.coarse = self.be.make_coarse_engine(an, am, self.domain, num_levels - self.D, cycle_type, pre, post,
-                                                 coarse_tolerance, coarse_max_iterations)
+                                                 coarse_tolerance, coarse_max_iterations,
+                                                 **({"shift": self.shift} if self.shift else {}))
+        self._kw = {"shift": self.shift} if self.shift else {}  # forwarded to every slab pass
         self.exchanges = 0
 
     # -- buffer roles (for CUDA-graph replay) ---------------------------------------------------------------
@@ -362,7 +375,7 @@ class DistributedCycleEngine:
         self.ensure(2 * self.pre + 2, ins)
         v = min(self.vdepth(t) for t, _ in ins)
         self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.pre, coefficient=-1.0, coarse_out=c.f[off:off + rows],
-                        u_zero=u_zero)
+                        u_zero=u_zero, **self._kw)
         b.u, b.tmp = b.tmp, b.u
         self.set_valid(b.u, v - 2 * self.pre)
         self.set_valid(c.f, (v - (2 * self.pre + 2)) // 2)
@@ -375,7 +388,7 @@ class DistributedCycleEngine:
                     effective=lambda d: min(d[0], d[1], 2 * d[2] - 1))
         v = min(self.vdepth(b.u), self.vdepth(b.f), 2 * self.vdepth(c.u) - 1)
         self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.post, coefficient=-1.0, coarse_in=c.u[off:off + rows],
-                        sumsq_out=sumsq_out if norm else None, norm_rows=s.own_local)
+                        sumsq_out=sumsq_out if norm else None, norm_rows=s.own_local, **self._kw)
         b.u, b.tmp = b.tmp, b.u
         self.set_valid(b.u, v - 2 * self.post)
 
@@ -474,11 +487,13 @@ class DistributedMixedPrecisionSolver:
             b.f[-1, :] = 0
 
     # -- solve loop ----------------------------------------------------------------------------------------------
-    def restart(self) -> float:
+    def restart(self, keep_iterate: bool = False) -> float:
+        """Begin a solve from u = 0, or (keep_iterate) from whatever the fp64 level-0 iterate holds."""
         eng = self.eng
         b64 = eng.bufs(0, torch.float64)
-        b64.u.zero_()
-        eng.set_valid(b64.u, eng.part.ghost)
+        if not keep_iterate:
+            b64.u.zero_()
+            eng.set_valid(b64.u, eng.part.ghost)
         self.phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
         self.history: List[float] = []
         if self.phase == "refine":
@@ -486,9 +501,9 @@ class DistributedMixedPrecisionSolver:
         if self.phase == "fp32":
             b32 = eng.bufs(0, torch.float32)
             b32.f.copy_(b64.f)
-            b32.u.zero_()
+            b32.u.copy_(b64.u)
             eng.set_valid(b32.f, eng.vdepth(b64.f))
-            eng.set_valid(b32.u, eng.part.ghost)
+            eng.set_valid(b32.u, eng.vdepth(b64.u))
         return float("nan")
 
     def _norm(self, slot: int) -> float:
@@ -506,14 +521,14 @@ class DistributedMixedPrecisionSolver:
             eng.ensure(1, [(b64.u, 0), (b32.u, 0), (b64.f, 0)])
             v = min(eng.vdepth(b64.u), eng.vdepth(b32.u))
             eng.be.vc_defect_pass(b64.u, b64.tmp, b64.f, s.hx, s.hy, e_in=b32.u, r_out=b32.f, sumsq_out=self.ss[1:2],
-                                  norm_rows=s.own_local)
+                                  norm_rows=s.own_local, **eng._kw)
             b64.u, b64.tmp = b64.tmp, b64.u
             eng.set_valid(b64.u, v)
         else:
             eng.ensure(1, [(b64.u, 0), (b64.f, 0)])
             v = eng.vdepth(b64.u)
             eng.be.vc_defect_pass(b64.u, None, b64.f, s.hx, s.hy, r_out=b32.f, sumsq_out=self.ss[1:2],
-                                  norm_rows=s.own_local)
+                                  norm_rows=s.own_local, **eng._kw)
         eng.set_valid(b32.f, min(v, eng.vdepth(b64.f)) - 1)
         eng.allreduce_sum(self.ss)
 
@@ -540,9 +555,9 @@ class DistributedMixedPrecisionSolver:
             self.phase = "fp64"
         return norm
 
-    def solve(self):
+    def solve(self, keep_iterate: bool = False):
         self.precision_switches = []
-        r0 = self.restart()
+        r0 = self.restart(keep_iterate)
         converged = False
         for _ in range(self.max_iterations):
             if self.step() < self.tolerance:
@@ -554,6 +569,159 @@ class DistributedMixedPrecisionSolver:
                    "final_residual": self.history[-1], "initial_residual": r0,
                    "precision_switches": list(self.precision_switches), "dist_levels": self.eng.D,
                    "num_levels": self.eng.num_levels, "halo_exchanges": self.eng.exchanges}
+
+
+# ======================================================================================================
+# Implicit heat stepping on row slabs (BASELINE configs[4]: one distributed shifted multigrid solve per step)
+# ======================================================================================================
+class DistributedHeatSolver:
+    """theta-method time stepping of u_t = alpha*lap(u) + f on row slabs, the multi-GPU twin of
+    `applications.heat_solver.HeatSolver2D` (same linear system, docs/methodology.md:710 divided by theta*alpha*dt:
+    (-lap_h + lambda) u^{n+1} = lambda*rhs, lambda = 1/(theta*alpha*dt); same result keys as the reference's
+    applications/heat_solver.py:227-247).  The iterate never leaves the slabs: per step every rank forms its rows of
+    the right-hand side, one all-reduce gives the rhs norm for the relative stopping test, and the shifted
+    mixed-precision solve starts from u^n.  No reference oracle exists for this row: parity unpinned,
+    validated against the single-GPU solver (bit-identical owned rows) and the analytical solutions."""
+
+    def __init__(self, *, max_iterations: int = 50, tolerance: float = 1e-8, cycle_type: str = "V",
+                 precision_strategy: str = "adaptive", backend=None, device=None, use_cuda_graphs: bool = False,
+                 **engine_kw):
+        if precision_strategy in ("single", "fp32"):
+            raise ValueError("the heat driver keeps the fp64 iterate between steps: use 'adaptive', 'refinement' or 'double'")
+        self.max_iterations, self.tolerance, self.cycle_type = max_iterations, tolerance, cycle_type
+        self.precision_strategy, self.backend, self.device = precision_strategy, backend, device
+        self.use_cuda_graphs, self.engine_kw = use_cuda_graphs, engine_kw
+        self._solvers: Dict[Tuple, DistributedMixedPrecisionSolver] = {}
+        self.time_history: List[Dict[str, Any]] = []
+
+    @staticmethod
+    def _theta(cfg) -> float:
+        m = getattr(cfg.method, "value", cfg.method)
+        if m == "backward_euler":
+            return 1.0
+        if m == "crank_nicolson":
+            return 0.5
+        if m == "theta_method":
+            if not 0.0 < cfg.theta <= 1.0:
+                raise ValueError("theta must be in (0, 1] for an implicit step")
+            return cfg.theta
+        raise ValueError(f"Unknown time stepping method: {cfg.method}")
+
+    def _solver(self, nx, ny, domain, lam) -> "DistributedMixedPrecisionSolver":
+        key = (nx, ny, tuple(domain), lam)
+        sol = self._solvers.get(key)
+        if sol is None:
+            sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=self.precision_strategy,
+                                                  tolerance=self.tolerance, max_iterations=self.max_iterations,
+                                                  cycle_type=self.cycle_type, shift=lam, backend=self.backend,
+                                                  device=self.device, use_cuda_graphs=self.use_cuda_graphs,
+                                                  **self.engine_kw)
+            self._solvers[key] = sol
+        return sol
+
+    def solve_heat_problem(self, problem, nx: int, ny: int, time_config, gather: bool = True) -> Dict[str, Any]:
+        import time
+        domain = tuple(float(v) for v in problem.domain)
+        alpha, theta = float(problem.thermal_diffusivity), self._theta(time_config)
+        dt, t_cur, step, total_mg = float(time_config.dt), 0.0, 0, 0
+        sol = self._solver(nx, ny, domain, 1.0 / (theta * alpha * dt))
+        eng, s = sol.eng, sol.s0
+        G = eng.part.ghost
+        lo, hi = s.own_local
+        x = domain[0] + (s.row0 + np.arange(s.loc_nx)) * s.hx
+        y = domain[2] + np.arange(ny) * s.hy
+        X, Y = np.meshgrid(x, y, indexing="ij")  # the slab's rows of Grid.X / Grid.Y (core/grid.py:50), ghosts included
+
+        def to_slab(a, like):
+            t = torch.from_numpy(np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), X.shape)))
+            return t.to(like.device)
+
+        def source(t):
+            if problem.source_function is None:
+                return None
+            f = np.asarray(problem.source_function(X, Y, t), dtype=np.float64)
+            return f if f.any() else None
+
+        b = eng.bufs(0, torch.float64)
+        b.u.copy_(to_slab(problem.initial_condition(X, Y), b.u))
+        b.u[:, 0] = 0
+        b.u[:, -1] = 0
+        if s.own_lo == 0:
+            b.u[0, :] = 0
+        if s.own_hi == s.nx_glob:
+            b.u[-1, :] = 0
+        eng.set_valid(b.u, G)  # evaluated on the ghost rows as well
+        f_old = source(0.0) if theta < 1.0 else None
+        solver_time, t_start = 0.0, time.time()
+        while t_cur < time_config.t_final - 1e-14:
+            if t_cur + dt > time_config.t_final:
+                dt = time_config.t_final - t_cur
+            step += 1
+            t_new = t_cur + dt
+            lam = 1.0 / (theta * alpha * dt)
+            nsol = self._solver(nx, ny, domain, lam)
+            if nsol is not sol:  # shortened last step: another shift, hence another solver; hand the iterate over
+                nb = nsol.eng.bufs(0, torch.float64)
+                nb.u.copy_(eng.bufs(0, torch.float64).u)
+                nsol.eng.set_valid(nb.u, eng.vdepth(eng.bufs(0, torch.float64).u))
+                sol, eng = nsol, nsol.eng
+            t0 = time.time()
+            b = eng.bufs(0, torch.float64)
+            # rhs = lambda * (u + (1-theta) alpha dt lap_h u + dt (theta f_new + (1-theta) f_old)) on the local rows
+            v = eng.vdepth(b.u)
+            if theta < 1.0:
+                eng.ensure(1, [(b.u, 0)])
+                v = eng.vdepth(b.u) - 1  # lap_h of a ghost row needs the next one
+            b.f.copy_(b.u)
+            if theta < 1.0:
+                b.f.add_(eng.be.apply_laplacian(b.u, s.hx, s.hy), alpha=(1.0 - theta) * alpha * dt)
+            f_new = source(t_new)
+            if f_new is not None:
+                b.f.add_(to_slab(f_new, b.f), alpha=dt * theta)
+            if theta < 1.0 and f_old is not None:
+                b.f.add_(to_slab(f_old, b.f), alpha=dt * (1.0 - theta))
+            b.f.mul_(lam)
+            eng.set_valid(b.f, v)
+            sol.zero_boundary_ring_of_rhs()
+            # relative stopping test against the GLOBAL rhs norm: the right-hand side scales with lambda
+            ss = eng.allreduce_sum(eng.be.sumsq(b.f[lo:hi]))
+            scale = float(np.sqrt(s.hx * s.hy * float(ss.item())))
+            sol.tolerance = self.tolerance * max(scale, 1e-300)
+            sol.switch_threshold = max(1e-6 * scale, sol.tolerance)
+            _, info = sol.solve(keep_iterate=True)
+            solver_time += time.time() - t0
+            total_mg += info["iterations"]
+            f_old, t_cur = f_new, t_new
+        total = time.time() - t_start
+        u_loc = eng.bufs(0, torch.float64).u
+        errors: Dict[str, Any] = {}
+        results: Dict[str, Any] = {
+            "problem_name": problem.name, "grid_size": (nx, ny),
+            "time_config": {"method": getattr(time_config.method, "value", time_config.method),
+                            "dt_initial": time_config.dt, "dt_final": dt, "t_final": time_config.t_final,
+                            "adaptive_dt": time_config.adaptive_dt},
+            "final_solution": eng.gather_solution(u_loc).cpu().numpy() if gather else None,
+            "local_solution": u_loc[lo:hi], "local_rows": (s.own_lo, s.own_hi),
+            "final_time": t_cur, "total_steps": step, "total_time": total, "total_solver_time": solver_time,
+            "avg_mg_iterations": total_mg / step if step else 0, "total_mg_iterations": total_mg, "errors": errors,
+            "solver_type": "multigrid", "use_gpu": u_loc.is_cuda, "n_gpus": eng.world,
+            "halo_exchanges": sum(sv.eng.exchanges for sv in self._solvers.values()),
+        }
+        if problem.analytical_solution is not None:
+            exact = to_slab(problem.analytical_solution(X, Y, t_cur), u_loc)[lo:hi]
+            err = u_loc[lo:hi] - exact
+            acc = torch.stack([(err ** 2).sum(), (exact ** 2).sum()]).to(torch.float64)
+            eng.allreduce_sum(acc)
+            mx = torch.stack([err.abs().max(), exact.abs().max()]).to(torch.float64)
+            if eng.world > 1:
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=eng.group)
+            l2e, l2n = float(np.sqrt(acc[0].item() * s.hx * s.hy)), float(np.sqrt(acc[1].item() * s.hx * s.hy))
+            errors.update({"l2_error": l2e, "relative_l2_error": l2e / l2n if l2n > 0 else l2e,
+                           "max_error": float(mx[0].item()),
+                           "relative_max_error": float(mx[0].item() / mx[1].item()) if mx[1].item() > 0 else float(mx[0].item()),
+                           "grid_spacing": (s.hx, s.hy)})
+        self.time_history.append(results)
+        return results
 
 
 # ======================================================================================================

@@ -234,12 +234,17 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
             sweeps: int = 2, omega: float = 1.0, coefficient: float = -1.0,
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
             sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
-            u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0) -> None:
-    """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS sweeps -> [coarse_out = R(f - A u)] or
-    [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None: nothing stored).
-    ``u_zero``: treat u_in as identically zero without reading it."""
+            u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0,
+            smoother: str = "rbgs") -> None:
+    """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS (``smoother="jacobi"``: damped Jacobi) sweeps ->
+    [coarse_out = R(f - A u)] or [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None:
+    nothing stored).  ``u_zero``: treat u_in as identically zero without reading it."""
     nx, ny = f.shape
     flags = (rows & 0xFFF) << 8
+    if smoother == "jacobi":
+        flags |= _lib.VC_JACOBI
+    elif smoother != "rbgs":
+        raise ValueError(f"vc_pass: smoother must be 'rbgs' or 'jacobi', got {smoother!r}")
     if coarse_in is not None:
         flags |= _lib.VC_PROLONG
     if coarse_out is not None:
@@ -267,7 +272,7 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
               hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, nlo, nhi, shift, stream_ptr())
     if timed:
         ev1.record()
-        tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"rbgs{sweeps}"
+        tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"{'jac' if smoother == 'jacobi' else 'rbgs'}{sweeps}"
                + ("+R" if coarse_out is not None else "") + ("+N" if sumsq_out is not None else "")
                + f"/{'f64' if f.dtype == torch.float64 else 'f32'}/{nx}x{ny}")
         TIMER.records.append((tag, ev0, ev1))

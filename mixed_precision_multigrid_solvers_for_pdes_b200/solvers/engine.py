@@ -9,8 +9,8 @@ sequence of one V/W/F cycle exactly in the order of the reference recursion
 
 Two kernel sets implement the same sequence:
   * ``basic``  -- one launch per reference method (strict arithmetic; also the on-GPU cross-check);
-  * ``fused``  -- temporally blocked red-black GS with fused residual+restriction and fused
-                 prolongation+correction+post-smooth (mg_vcycle.cu), used when available.
+  * ``fused``  -- temporally blocked red-black GS / damped Jacobi with fused residual+restriction and
+                 fused prolongation+correction+post-smooth (mg_stream.cuh), used when available.
 No host synchronisation happens inside a cycle, so a cycle can be captured in a CUDA graph."""
 from __future__ import annotations
 
@@ -127,12 +127,15 @@ class CycleEngine:
         if self.kernels == "basic":
             return False
         op = self.operators[lvl]
-        ok = (getattr(self.smoother, "kind", None) == "rbgs" and type(op).__name__ in _NATIVE_OPERATORS
+        kind = getattr(self.smoother, "kind", None)
+        # Jacobi: TMA-staged instantiations only, and (like the strict kernel) no Helmholtz shift
+        jac = kind == "jacobi" and self.loader == "tma" and not getattr(op, "shift", 0.0)
+        ok = ((kind == "rbgs" or jac) and type(op).__name__ in _NATIVE_OPERATORS
               and getattr(self.restriction_ops[lvl], "method", None) == "full_weighting"
               and getattr(self.prolongation_ops[lvl], "method", None) == "bilinear"
               and torch_dtype(level_dtypes[lvl]) == torch_dtype(level_dtypes[lvl + 1]))
         if not ok and self.kernels == "fused":
-            raise ValueError("kernels='fused' needs GaussSeidelSmoother(red_black=True), LaplacianOperator, "
+            raise ValueError("kernels='fused' needs GaussSeidelSmoother(red_black=True) or a Jacobi smoother, LaplacianOperator, "
                              "full_weighting restriction, bilinear prolongation and one dtype per level pair")
         return ok
 
@@ -185,6 +188,7 @@ class CycleEngine:
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
         coeff, omega, ld = self.operators[lvl].coefficient, self.smoother.omega, self.loader
+        sk = self.smoother.kind  # "rbgs" or "jacobi": same passes, the sweeps differ
         sh = getattr(self.operators[lvl], "shift", 0.0)
         # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
         n = self.pre
@@ -192,13 +196,13 @@ class CycleEngine:
             b.u.zero_()  # nothing will overwrite the iterate before it is read
             u_zero = False
         while n > 2:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero, shift=sh)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero, shift=sh, smoother=sk)
             b.u, b.tmp = b.tmp, b.u
             n -= 2
             u_zero = False
         if n > 0:
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld,
-                        u_zero=u_zero, shift=sh)
+                        u_zero=u_zero, shift=sh, smoother=sk)
             b.u, b.tmp = b.tmp, b.u
         else:
             ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld, shift=sh)
@@ -210,14 +214,14 @@ class CycleEngine:
         first = min(n, 2)
         last = (n - first) == 0
         ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, omega=omega, coefficient=coeff, coarse_in=c.u,
-                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh)
+                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh, smoother=sk)
         b.u, b.tmp = b.tmp, b.u
         n -= first
         while n > 0:
             k = min(n, 2)
             n -= k
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, omega=omega, coefficient=coeff,
-                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh)
+                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh, smoother=sk)
             b.u, b.tmp = b.tmp, b.u
 
     # -- the recursion ------------------------------------------------------------------------------

@@ -14,9 +14,9 @@ def _np(t):
 
 
 class _CoarseEmu:
-    def __init__(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max):
+    def __init__(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0):
         self.args = dict(max_levels=levels, cycle_type=cycle_type, pre=pre, post=post, coarse_tolerance=coarse_tol,
-                         coarse_max_iterations=coarse_max, domain=domain)
+                         coarse_max_iterations=coarse_max, domain=domain, shift=shift)
         self.nx, self.ny = nx, ny
         self._b = {}
 
@@ -50,11 +50,17 @@ class OracleBackend:
     def scalar(self, n=1):
         return torch.zeros(n, dtype=torch.float64)
 
-    def make_coarse_engine(self, *a):
-        return _CoarseEmu(*a)
+    def make_coarse_engine(self, *a, **k):
+        return _CoarseEmu(*a, **k)
+
+    def sumsq(self, t):
+        return (t.to(torch.float64) ** 2).sum().reshape(1)
+
+    def apply_laplacian(self, u, hx, hy):
+        return torch.from_numpy(O.apply_laplacian(_np(u), hx, hy, 1.0))
 
     def vc_pass(self, u_in, u_out, f, hx, hy, *, sweeps=2, omega=1.0, coefficient=-1.0, coarse_in=None,
-                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0):
+                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0):
         F = _np(f)
         nx = F.shape[0]
         nxo = nx if nx % 2 == 1 else nx - 1
@@ -62,11 +68,11 @@ class OracleBackend:
         if coarse_in is not None:
             C = _np(coarse_in)[:(nxo - 1) // 2 + 1]
             U[:nxo] += O.prolong(C)
-        U = O.rbgs_smooth(U, F, hx, hy, omega, sweeps)
+        U = O.rbgs_smooth(U, F, hx, hy, omega, sweeps, shift)
         if u_out is not None:
             u_out.copy_(torch.from_numpy(U))
         if coarse_out is not None or sumsq_out is not None:
-            R = O.residual(U, F, hx, hy, coefficient)
+            R = O.residual(U, F, hx, hy, coefficient, shift)
             if coarse_out is not None:
                 rc = O.restrict(R[:nxo])
                 coarse_out[:rc.shape[0]].copy_(torch.from_numpy(rc))
@@ -75,13 +81,13 @@ class OracleBackend:
                 sumsq_out[0] = float(np.sum(R[lo:hi].astype(np.float64) ** 2))
 
     def vc_defect_pass(self, u_in, u_out, f, hx, hy, *, e_in=None, r_out=None, sumsq_out=None, coefficient=-1.0,
-                       norm_rows=None, rows=0):
+                       norm_rows=None, rows=0, shift=0.0):
         U = _np(u_in).copy()
         if e_in is not None:
             U = U + _np(e_in).astype(np.float64)
             u_out.copy_(torch.from_numpy(U))
         if r_out is not None:
-            R = O.residual(U, _np(f), hx, hy, coefficient)
+            R = O.residual(U, _np(f), hx, hy, coefficient, shift)
             r_out.copy_(torch.from_numpy(R.astype(np.float32)))
             lo, hi = norm_rows if norm_rows is not None else (0, U.shape[0])
             sumsq_out[0] = float(np.sum(R[lo:hi] ** 2))

@@ -44,6 +44,17 @@ def main():
                          "u": full.cpu().numpy()}
         res["exchanges"] = info["halo_exchanges"]
         res["D"] = sol.eng.D
+    # BASELINE configs[4] on slabs: 3 backward-Euler steps + a shortened 4th, one shifted solve per step, graphs on
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import HeatProblem, TimeSteppingConfig, TimeSteppingMethod
+    from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
+    kx, ky = np.pi / 2.0, np.pi
+    mode = lambda X, Y: np.sin(kx * X) * np.sin(ky * Y)  # noqa: E731
+    prob = HeatProblem("decay", mode, None, lambda X, Y, t: mode(X, Y) * np.exp(-(kx ** 2 + ky ** 2) * t), domain=dom)
+    hs = DistributedHeatSolver(tolerance=1e-9, agglomerate_below=129, device=dev, use_cuda_graphs=True)
+    r = hs.solve_heat_problem(prob, nx, ny, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt=0.002, t_final=0.007))
+    res["heat"] = {"u": r["final_solution"], "iters": r["total_mg_iterations"], "steps": r["total_steps"],
+                   "errors": r["errors"], "exchanges": r["halo_exchanges"]}
+    del hs, r
     if dist.get_rank() == 0:
         torch.save(res, sys.argv[1])
     # captured graphs hold NCCL work: release them before tearing the communicator down

@@ -79,6 +79,14 @@ def _worker(rank, world, port, case, out):
                 norms.append(float(np.sqrt(s.hx * s.hy * ss.item())))
             u = eng.gather_solution(eng.bufs(0, torch.float64).u)
             res = {"norms": norms, "u": u.numpy(), "D": eng.D, "L": eng.num_levels, "ex": eng.exchanges}
+        elif case["kind"] == "heat":
+            from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
+            hs = DistributedHeatSolver(tolerance=case["tol"], precision_strategy=case["strategy"],
+                                       agglomerate_below=case["agg"], backend=OracleBackend())
+            r = hs.solve_heat_problem(_heat_problem(dom, case.get("source", False)), nx, ny, _time_config(case))
+            res = {"u": r["final_solution"], "iters": r["total_mg_iterations"], "steps": r["total_steps"],
+                   "errors": r["errors"], "t": r["final_time"], "ex": r["halo_exchanges"], "rows": r["local_rows"],
+                   "keys": sorted(r.keys())}
         else:
             sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=case["strategy"],
                                                   tolerance=1e-8, agglomerate_below=case["agg"], backend=OracleBackend())
@@ -90,6 +98,25 @@ def _worker(rank, world, port, case, out):
             torch.save(res, out)
     finally:
         dist.destroy_process_group()
+
+
+def _heat_problem(dom, with_source=False):
+    """u = sin(kx x) sin(ky y) exp(-alpha (kx^2+ky^2) t) [+ a steady forced mode], zero on the boundary of `dom`."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import HeatProblem
+    kx, ky, alpha = np.pi / (dom[1] - dom[0]), np.pi / (dom[3] - dom[2]), 0.7
+    mode = lambda x, y: np.sin(kx * (x - dom[0])) * np.sin(ky * (y - dom[2]))  # noqa: E731
+    k2 = kx ** 2 + ky ** 2
+    if not with_source:
+        return HeatProblem("decay", mode, None, lambda x, y, t: mode(x, y) * np.exp(-alpha * k2 * t),
+                           thermal_diffusivity=alpha, domain=dom)
+    # u = mode * (1 + t): u_t - alpha lap u = mode * (1 + alpha k2 (1 + t))
+    return HeatProblem("forced", mode, lambda x, y, t: mode(x, y) * (1 + alpha * k2 * (1 + t)),
+                       lambda x, y, t: mode(x, y) * (1 + t), thermal_diffusivity=alpha, domain=dom)
+
+
+def _time_config(case):
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import TimeSteppingConfig, TimeSteppingMethod
+    return TimeSteppingConfig(TimeSteppingMethod(case["method"]), dt=case["dt"], t_final=case["t_final"])
 
 
 def _run(world, case, tmp_path):
@@ -134,3 +161,47 @@ def test_two_rank_mixed_precision_solve(tmp_path):
     assert [s["iteration"] for s in r2["switches"]] == [s["iteration"] for s in r1["switches"]]
     exact = np.sin(np.pi * np.linspace(0, 2, 257))[:, None] * np.sin(np.pi * np.linspace(0, 1, 129))[None, :]
     assert np.max(np.abs(r2["u"] - exact)) < 2e-4
+
+
+@pytest.mark.parametrize("method,strategy", [("backward_euler", "double"), ("crank_nicolson", "adaptive")])
+def test_two_rank_heat_steps_equal_one_rank(tmp_path, method, strategy):
+    """BASELINE configs[4] host logic: theta-method stepping on row slabs, one shifted distributed solve per step.
+    2 ranks == 1 rank bit for bit (same cycle counts), the last (shortened) step included."""
+    case = dict(kind="heat", nx=257, ny=129, domain=(0.0, 2.0, 0.0, 1.0), agg=33, method=method, strategy=strategy,
+                dt=0.004, t_final=0.015, tol=1e-9, source=(method == "crank_nicolson"))
+    r2 = _run(2, case, tmp_path)
+    r1 = _run(1, case, tmp_path)
+    assert r2["steps"] == r1["steps"] == 4 and abs(r2["t"] - 0.015) < 1e-14
+    assert r2["iters"] == r1["iters"] and r2["ex"] > 0
+    assert np.array_equal(r2["u"], r1["u"])
+    for k in ("l2_error", "relative_l2_error", "max_error", "relative_max_error"):
+        assert abs(r2["errors"][k] - r1["errors"][k]) <= 1e-12 * abs(r1["errors"][k])
+    # accuracy: O(dt) resp. O(dt^2) + O(h^2) against the analytical solution
+    assert r2["errors"]["relative_max_error"] < (4e-3 if method == "backward_euler" else 2e-4)
+    for key in ("problem_name", "grid_size", "time_config", "final_solution", "final_time", "total_steps", "total_time",
+                "total_solver_time", "avg_mg_iterations", "total_mg_iterations", "errors", "solver_type", "use_gpu"):
+        assert key in r2["keys"], key  # result keys of applications/heat_solver.py:227-247
+
+
+def test_heat_fp64_step_equals_single_process_oracle(tmp_path):
+    """One rank, fp64 strategy: every step is exactly the oracle's shifted multigrid solve started from u^n."""
+    dom = (0.0, 2.0, 0.0, 1.0)
+    case = dict(kind="heat", nx=129, ny=65, domain=dom, agg=17, method="backward_euler", strategy="double", dt=0.01,
+                t_final=0.03, tol=1e-9)
+    r = _run(2, case, tmp_path)
+    prob = _heat_problem(dom)
+    g = O.OGrid(129, 65, dom)
+    x, y = g.coords()
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    u = prob.initial_condition(X, Y)
+    u[0, :] = u[-1, :] = 0
+    u[:, 0] = u[:, -1] = 0
+    lam, iters = 1.0 / (prob.thermal_diffusivity * 0.01), 0
+    for _ in range(3):
+        rhs = lam * u
+        scale = O.l2_norm(rhs, g.hx, g.hy)
+        s = O.OracleMultigrid(129, 65, max_levels=5, max_iterations=50, tolerance=1e-9 * scale, domain=dom, shift=lam)
+        u, info = s.solve(rhs, initial_guess=u)
+        iters += info["iterations"]
+    assert r["iters"] == iters
+    assert np.max(np.abs(r["u"] - u)) <= 1e-13 * np.max(np.abs(u))

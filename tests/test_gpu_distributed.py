@@ -34,6 +34,26 @@ def test_world1_distributed_engine_equals_oracle():
         assert abs(err - O.mms_discretisation_error(n)) <= 0.01 * O.mms_discretisation_error(n)
 
 
+def test_world1_distributed_heat_equals_single_gpu_heat_solver():
+    """The slab heat driver (world = 1) against HeatSolver2D on the same problem: same steps, same accuracy."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import (HeatProblem, HeatSolver2D, TimeSteppingConfig,
+                                                                 TimeSteppingMethod)
+    from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
+    n, alpha = 257, 0.5
+    mode = lambda X, Y: np.sin(np.pi * X) * np.sin(np.pi * Y)  # noqa: E731
+    exact = lambda X, Y, t: mode(X, Y) * np.exp(-2 * np.pi ** 2 * alpha * t)  # noqa: E731
+    prob = HeatProblem("pure_diffusion", mode, None, exact, thermal_diffusivity=alpha)
+    for method, bound in ((TimeSteppingMethod.BACKWARD_EULER, 1e-2), (TimeSteppingMethod.CRANK_NICOLSON, 2e-4)):
+        cfg = TimeSteppingConfig(method, dt=0.005, t_final=0.02)
+        rd = DistributedHeatSolver(tolerance=1e-10, agglomerate_below=33, device=torch.device("cuda", 0),
+                                   use_cuda_graphs=True).solve_heat_problem(prob, n, n, cfg)
+        rs = HeatSolver2D(tolerance=1e-10).solve_heat_problem(prob, n, n, cfg)
+        assert rd["total_steps"] == rs["total_steps"] == 4
+        assert np.max(np.abs(rd["final_solution"] - rs["final_solution"])) <= 1e-8
+        assert rd["errors"]["relative_max_error"] < bound
+        assert abs(rd["errors"]["max_error"] - rs["errors"]["max_error"]) <= 1e-6 * rs["errors"]["max_error"] + 1e-9
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_gpus_equal_one_gpu(tmp_path):
     out = str(tmp_path / "res.pt")
@@ -54,3 +74,8 @@ def test_two_gpus_equal_one_gpu(tmp_path):
         np.testing.assert_allclose(r2[key]["history"], r1[key]["history"], rtol=1e-10)
         assert np.array_equal(r1[key]["u"], r2[key]["u"]), key   # owned rows bit-identical across GPU counts
     assert r2["exchanges"] > 0
+    # heat stepping on slabs (configs[4]): same steps, same cycle counts, bit-identical field, O(dt) accurate
+    h1, h2 = r1["heat"], r2["heat"]
+    assert h1["steps"] == h2["steps"] == 4 and h1["iters"] == h2["iters"] and h2["exchanges"] > 0
+    assert np.array_equal(h1["u"], h2["u"])
+    assert h2["errors"]["relative_max_error"] < 2e-3

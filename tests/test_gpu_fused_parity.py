@@ -110,6 +110,90 @@ def test_prolong_correct_smooth_norm_pass(n, m, pow2, dt, loader):
         assert torch.equal(out, out2)
 
 
+JAC_SHAPES = [(129, 129, True), (257, 513, False), (33, 17, False), (5, 5, True), (9, 241, False), (1025, 129, False),
+              (513, 513, True)]
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m,pow2", JAC_SHAPES)
+def test_jacobi_passes(n, m, pow2, dt):
+    """Damped Jacobi in the streaming kernel (MG_VC_JACOBI): plain sweeps, sweeps + residual + restriction,
+    prolongation + correction + sweeps + norm, and the zero-iterate flag, against the oracle (smoothers.py:41-86).
+    The relaxation blend is not contracted, so square power-of-two grids are bit-exact for EVERY omega."""
+    dom = (0.0, 1.0, 0.0, 1.0) if (pow2 or n in (257, 33, 1025)) else (0.0, 1.3, -0.2, 0.9)
+    _, u, f = _fields(n, m, dt, 21)
+    g = Grid(n, m, dom, dt)
+    nc, mc = (n - 1) // 2 + 1, (m - 1) // 2 + 1
+    ec = np.random.default_rng(22).uniform(-1, 1, (nc, mc)).astype(dt)
+    du, df, dec = to_device(u)[0], to_device(f)[0], to_device(ec)[0]
+    zeros = np.zeros_like(u)
+    for sweeps in (1, 2):
+        for omega in (2.0 / 3.0, 0.8, 1.0):
+            what = f"jacobi {n}x{m} {dt.__name__} s={sweeps} w={omega:.3f}"
+            out = empty_field(n, m, dt)
+            ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=sweeps, omega=omega, smoother="jacobi")
+            us = O.jacobi_smooth(u, f, g.hx, g.hy, omega, sweeps)
+            _cmp(out, us, pow2, what + " smooth")
+            # down pass
+            out = empty_field(n, m, dt)
+            rc = empty_field(nc, mc, dt)
+            rc.fill_(7.0)
+            ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=sweeps, omega=omega, coarse_out=rc, smoother="jacobi")
+            _cmp(out, us, pow2, what + " u of the down pass")
+            _cmp(rc, O.restrict(O.residual(us, f, g.hx, g.hy, -1.0)), pow2, what + " restricted residual")
+            # down pass from the zero iterate (iterate buffer poisoned, must not be read)
+            out.fill_(float("nan"))
+            poison = torch.full_like(out, float("nan"))
+            ops.vc_pass(poison, out, df, g.hx, g.hy, sweeps=sweeps, omega=omega, coarse_out=rc, smoother="jacobi",
+                        u_zero=True)
+            uz = O.jacobi_smooth(zeros, f, g.hx, g.hy, omega, sweeps)
+            _cmp(out, uz, pow2, what + " u from zero")
+            _cmp(rc, O.restrict(O.residual(uz, f, g.hx, g.hy, -1.0)), pow2, what + " restricted residual from zero")
+            # up pass
+            ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+            out = empty_field(n, m, dt)
+            ops.vc_pass(du, out, df, g.hx, g.hy, sweeps=sweeps, omega=omega, coarse_in=dec, sumsq_out=ss,
+                        smoother="jacobi")
+            up = O.jacobi_smooth(u + O.prolong(ec), f, g.hx, g.hy, omega, sweeps)
+            _cmp(out, up, pow2, what + " up pass")
+            r = O.residual(up, f, g.hx, g.hy, -1.0)
+            exp_ss = float(np.sum(r.astype(np.float64) ** 2))
+            assert abs(ss.item() - exp_ss) <= (1e-12 if dt is np.float64 else 1e-5) * exp_ss, what
+            out2 = empty_field(n, m, dt)
+            ops.vc_pass(du, out2, df, g.hx, g.hy, sweeps=sweeps, omega=omega, coarse_in=dec, smoother="jacobi")
+            assert torch.equal(out, out2), what
+    assert np.array_equal(to_host(du), u)
+
+
+def test_jacobi_large_grid_against_basic_kernels():
+    """4097^2: fused Jacobi passes == the strict one-launch-per-sweep kernel, bit for bit, any tile height."""
+    n = 4097
+    g = Grid(n, n)
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    for dt in (torch.float64, torch.float32):
+        u, f = empty_field(n, n, dt), empty_field(n, n, dt)
+        u.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        f.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
+        ref = u.clone()
+        ops.smooth_jacobi_(ref, f, g.hx, g.hy, 2.0 / 3.0, 2)
+        rref = ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0))
+        for rows in (0, 64):
+            out = empty_field(n, n, dt)
+            rc = empty_field(2049, 2049, dt)
+            ops.vc_pass(u, out, f, g.hx, g.hy, sweeps=2, omega=2.0 / 3.0, coarse_out=rc, smoother="jacobi", rows=rows)
+            assert torch.equal(out, ref)
+            assert torch.equal(rc, rref)
+
+
+def test_jacobi_needs_the_tma_loader():
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MGLibraryError
+    a, b = empty_field(33, 33, np.float64), empty_field(33, 33, np.float64)
+    with pytest.raises(MGLibraryError):
+        ops.vc_pass(a, b, a, 0.1, 0.1, smoother="jacobi", loader="cp_async")
+    with pytest.raises(ValueError, match="smoother"):
+        ops.vc_pass(a, b, a, 0.1, 0.1, smoother="sor")
+
+
 @pytest.mark.parametrize("rows", [32, 64, 128])
 def test_tile_height_does_not_change_results(rows):
     n = 513

@@ -23,10 +23,12 @@ def _smoother(kind):
 def test_fused_path_is_taken_and_required_config_enforced():
     g = Grid(65, 65)
     op = LaplacianOperator(-1.0)
-    s = MultigridSolver(max_levels=5, kernels="fused")
-    s.setup(g, op, RestrictionOperator(), ProlongationOperator(), smoother=JacobiSmoother())
-    with pytest.raises(ValueError, match="kernels='fused'"):
-        s.solve(g, op, O.mms_rhs(65))
+    # lexicographic GS (the setup default) has no fused pass; Jacobi has one with the TMA loader only
+    for kw, sm in (({}, None), ({"loader": "cp_async"}, JacobiSmoother())):
+        s = MultigridSolver(max_levels=5, kernels="fused", **kw)
+        s.setup(g, op, RestrictionOperator(), ProlongationOperator(), smoother=sm)
+        with pytest.raises(ValueError, match="kernels='fused'"):
+            s.solve(g, op, O.mms_rhs(65))
     for loader in ("tma", "cp_async"):
         s = MultigridSolver(max_levels=5, kernels="fused", loader=loader)
         s.setup(g, op, RestrictionOperator(), ProlongationOperator(), smoother=GaussSeidelSmoother(red_black=True))
@@ -35,6 +37,29 @@ def test_fused_path_is_taken_and_required_config_enforced():
         assert info["iterations"] == oinfo["iterations"] == 8
         np.testing.assert_allclose(info["residual_history"], oinfo["residual_history"], rtol=1e-12)
         assert np.max(np.abs(u - ou)) <= 1e-12 * np.max(np.abs(ou))
+
+
+@pytest.mark.parametrize("cls,omega", [(JacobiSmoother, 2.0 / 3.0), (WeightedJacobiSmoother, 0.8)])
+@pytest.mark.parametrize("pre,post", [(2, 2), (1, 3)])
+def test_fused_jacobi_solves(cls, omega, pre, post):
+    """Jacobi smoothing through the streaming kernel: same counts / histories / solutions as the oracle (13 and
+    11 cycles at 65^2 V(2,2)), and bit-for-bit the result of the strict per-sweep kernels."""
+    n = 65
+    g = Grid(n, n)
+    op = LaplacianOperator(-1.0)
+    runs = {}
+    for kernels in ("fused", "basic"):
+        s = MultigridSolver(max_levels=5, pre_smooth_iterations=pre, post_smooth_iterations=post, kernels=kernels)
+        s.setup(g, op, RestrictionOperator(), ProlongationOperator(), smoother=cls())
+        runs[kernels] = s.solve(g, op, O.mms_rhs(n))
+    u, info = runs["fused"]
+    ou, oinfo = O.OracleMultigrid(n, max_levels=5, pre=pre, post=post, smoother="jacobi", omega=omega).solve(O.mms_rhs(n))
+    assert info["iterations"] == oinfo["iterations"] == runs["basic"][1]["iterations"]
+    if (pre, post) == (2, 2):
+        assert info["iterations"] == (13 if omega < 0.7 else 11)
+    np.testing.assert_allclose(info["residual_history"], oinfo["residual_history"], rtol=1e-11)
+    assert np.max(np.abs(u - ou)) <= 1e-12 * np.max(np.abs(ou))
+    assert np.max(np.abs(u - runs["basic"][0])) <= 1e-12 * np.max(np.abs(ou))
 
 
 @pytest.mark.parametrize("pre,post", [(1, 1), (3, 2), (0, 2), (2, 0), (5, 4)])

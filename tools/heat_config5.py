@@ -1,8 +1,13 @@
-"""BASELINE config 5 on one GPU: backward-Euler heat equation, pure diffusion, n x n grid, `steps` time steps, one
-shifted multigrid solve per step.  Prints a JSON line (time per step, MG cycles per step, error vs analytical)."""
+"""BASELINE config 5: backward-Euler heat equation, pure diffusion, n x n grid, `steps` time steps, one shifted
+multigrid solve per step.  Prints a JSON line (time per step, MG cycles per step, error vs analytical).
+
+    python tools/heat_config5.py [n] [steps]                                      one GPU (HeatSolver2D)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        tools/heat_config5.py [n] [steps]                                         N GPUs, row slabs (DistributedHeatSolver)
+"""
 import json
-import sys
 import os
+import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,11 +19,43 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 dt = 1e-4
 prob = HeatTestProblems().get_problem("pure_diffusion")
 prob.source_function = None  # identically zero: skip the per-step host evaluation
-s = HeatSolver2D(tolerance=1e-8)
-t0 = time.time()
-res = s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * steps))
-wall = time.time() - t0
-print(json.dumps({"config": f"heat backward Euler {n}x{n}, {steps} steps, dt={dt}", "wall_s": round(wall, 3),
-                  "solver_s": round(res["total_solver_time"], 3), "ms_per_step": round(1e3 * res["total_solver_time"] / steps, 3),
-                  "avg_mg_cycles_per_step": res["avg_mg_iterations"], "max_error": res["errors"]["max_error"],
-                  "relative_max_error": res["errors"]["relative_max_error"]}))
+cfg = TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * steps)
+world = int(os.environ.get("WORLD_SIZE", "1"))
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    s = DistributedHeatSolver(tolerance=1e-8, device=dev, use_cuda_graphs=True)
+    s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 3), gather=False)  # warm-up: graphs captured
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.time()
+    res = s.solve_heat_problem(prob, n, n, cfg, gather=False)
+    torch.cuda.synchronize()
+    dist.barrier()
+    wall = time.time() - t0
+    rank = dist.get_rank()
+else:
+    s = HeatSolver2D(tolerance=1e-8)
+    t0 = time.time()
+    res = s.solve_heat_problem(prob, n, n, cfg)
+    wall = time.time() - t0
+    rank = 0
+if rank == 0:
+    print(json.dumps({"config": f"heat backward Euler {n}x{n}, {steps} steps, dt={dt}, {world} GPU(s)", "n_gpus": world,
+                      "wall_s": round(wall, 3), "solver_s": round(res["total_solver_time"], 3),
+                      "ms_per_step": round(1e3 * res["total_solver_time"] / steps, 3),
+                      "avg_mg_cycles_per_step": res["avg_mg_iterations"], "max_error": res["errors"]["max_error"],
+                      "relative_max_error": res["errors"]["relative_max_error"],
+                      "halo_exchanges": res.get("halo_exchanges")}))
+if world > 1:
+    del s, res
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
