@@ -79,6 +79,16 @@ def main():
                         e32 = empty_field(n, n, torch.float32); r32 = empty_field(n, n, torch.float32)
                         fn = (lambda: ops.vc_defect_pass(u, out, f, h, h, e_in=e32, r_out=r32, sumsq_out=ss, **kw))
                         byt, sw = 32.0, 0
+                    elif mode.startswith("jac") and loader == "tma":  # damped Jacobi (omega = 2/3) in the streaming kernel
+                        jk = dict(omega=2.0 / 3.0, smoother="jacobi", **kw)
+                        if mode == "jac2":
+                            fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, **jk)), 3 * w, 2
+                        elif mode == "jacdown2":
+                            fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_out=rc, **jk)), 3.25 * w, 2
+                        elif mode == "jacup2":
+                            fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, **jk)), 3.25 * w, 2
+                        else:
+                            continue
                     elif mode == "resrestrict":
                         fn, byt, sw = (lambda: ops.vc_pass(u, None, f, h, h, sweeps=0, coarse_out=rc, **kw)), 2.25 * w, 0
                     else:
@@ -92,6 +102,12 @@ def main():
         med, best = timeit(lambda: ops.smooth_rbgs_(out, f, h, h, 1.0, 2))
         print(json.dumps({"kernel": "basic_rbgs2", "dtype": dn, "n": n, "ms": round(med, 4),
                           "alg_smoother_GBs": round(3 * w * 2 * n * n / med / 1e6, 1)}), flush=True)
+        if any(m.startswith("jac") for m in a.modes.split(",")):
+            tmp = empty_field(n, n, dt)
+            med, best = timeit(lambda: ops.smooth_jacobi_(out, f, h, h, 2.0 / 3.0, 2, tmp=tmp))
+            print(json.dumps({"kernel": "basic_jacobi2", "dtype": dn, "n": n, "ms": round(med, 4),
+                              "alg_smoother_GBs": round(3 * w * 2 * n * n / med / 1e6, 1)}), flush=True)
+            del tmp
         del u, f, out, ec, rc
         torch.cuda.empty_cache()
 
