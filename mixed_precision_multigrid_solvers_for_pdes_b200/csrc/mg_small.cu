@@ -34,6 +34,7 @@ template <typename T, typename TC> struct Params {
   int cycle;  // 0 V, 1 W, 2 F
   int pre, post;
   int u_zero;
+  int iso1;  // hx == hy and omega == 1: the streaming kernel's 5-instruction point update (same bits as there)
   T* u;
   const T* f;
   int64_t ld_u, ld_f;
@@ -41,25 +42,30 @@ template <typename T, typename TC> struct Params {
 };
 
 using stream::relax_fast;
+using stream::relax_iso1;
 using stream::residual_fast;
+using stream::residual_iso;
 
 template <typename T>
-__device__ __forceinline__ T resid_at(const T* u, const T* f, int nx, int ny, int i, int j, const StencilScalars<T>& s) {
+__device__ __forceinline__ T resid_at(const T* u, const T* f, int nx, int ny, int i, int j, const StencilScalars<T>& s,
+                                      bool iso1) {
   const T fv = f[i * ny + j];
   if (i == 0 || i == nx - 1 || j == 0 || j == ny - 1) return fv;  // r = f on the boundary (laplacian.py:64,117)
   const T* p = u + i * ny + j;
-  return residual_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], fv);
+  return iso1 ? residual_iso<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], fv)
+              : residual_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], fv);
 }
 
 template <typename T>
-__device__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, int sweeps) {
+__device__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, int sweeps, bool iso1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = 0; k < sweeps; ++k)
     for (int c = 0; c < 2; ++c) {
       for (int i = 1 + warp; i <= nx - 2; i += THREADS / 32)      // rows over warps, columns over lanes
         for (int j = 1 + ((i + 1 + c) & 1) + 2 * lane; j <= ny - 2; j += 64) {
           T* p = u + i * ny + j;
-          p[0] = relax_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], f[i * ny + j]);
+          p[0] = iso1 ? relax_iso1<T>(s, p[ny], p[-ny], p[1], p[-1], f[i * ny + j])
+                      : relax_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], f[i * ny + j]);
         }
       __syncthreads();
     }
@@ -68,22 +74,22 @@ __device__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>
 // f_c = R(f - A u): injection on the coarse boundary, full weighting inside, reference summation order
 template <typename T, typename TO>
 __device__ void restrict_residual(const T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, TO* fc, int nxc,
-                                  int nyc) {
+                                  int nyc, bool iso1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int I = warp; I < nxc; I += THREADS / 32)
    for (int J = lane; J < nyc; J += 32) {
     const int idx = I * nyc + J, i = 2 * I, j = 2 * J;
     T v;
     if (I == 0 || I == nxc - 1 || J == 0 || J == nyc - 1) {
-      v = resid_at<T>(u, f, nx, ny, i, j, s);
+      v = resid_at<T>(u, f, nx, ny, i, j, s, iso1);
     } else {
-      const T nw = resid_at<T>(u, f, nx, ny, i - 1, j - 1, s), ne = resid_at<T>(u, f, nx, ny, i - 1, j + 1, s);
-      const T sw = resid_at<T>(u, f, nx, ny, i + 1, j - 1, s), se = resid_at<T>(u, f, nx, ny, i + 1, j + 1, s);
-      const T n_ = resid_at<T>(u, f, nx, ny, i - 1, j, s), s_ = resid_at<T>(u, f, nx, ny, i + 1, j, s);
-      const T w_ = resid_at<T>(u, f, nx, ny, i, j - 1, s), e_ = resid_at<T>(u, f, nx, ny, i, j + 1, s);
+      const T nw = resid_at<T>(u, f, nx, ny, i - 1, j - 1, s, iso1), ne = resid_at<T>(u, f, nx, ny, i - 1, j + 1, s, iso1);
+      const T sw = resid_at<T>(u, f, nx, ny, i + 1, j - 1, s, iso1), se = resid_at<T>(u, f, nx, ny, i + 1, j + 1, s, iso1);
+      const T n_ = resid_at<T>(u, f, nx, ny, i - 1, j, s, iso1), s_ = resid_at<T>(u, f, nx, ny, i + 1, j, s, iso1);
+      const T w_ = resid_at<T>(u, f, nx, ny, i, j - 1, s, iso1), e_ = resid_at<T>(u, f, nx, ny, i, j + 1, s, iso1);
       const T corners = ((nw + ne) + sw) + se;
       const T edges = ((n_ + s_) + w_) + e_;
-      v = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * resid_at<T>(u, f, nx, ny, i, j, s);
+      v = ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * resid_at<T>(u, f, nx, ny, i, j, s, iso1);
     }
     fc[idx] = (TO)v;
   }
@@ -221,13 +227,13 @@ __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC
         continue;
       }
       if (down) {
-        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.pre);
+        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.pre, p.iso1 != 0);
         const int nxc = p.nx[l + 1], nyc = p.ny[l + 1];
         if (l + 1 == last) {
-          restrict_residual<T, TC>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], fc, nxc, nyc);
+          restrict_residual<T, TC>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], fc, nxc, nyc, p.iso1 != 0);
           for (int k = threadIdx.x; k < nxc * nyc; k += THREADS) uc[k] = (TC)0;
         } else {
-          restrict_residual<T, T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], F(l + 1), nxc, nyc);
+          restrict_residual<T, T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], F(l + 1), nxc, nyc, p.iso1 != 0);
           for (int k = threadIdx.x; k < nxc * nyc; k += THREADS) U(l + 1)[k] = (T)0;
         }
         __syncthreads();
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC
         }
         if (l + 1 == last) prolong_add<T, TC>(U(l), p.nx[l], p.ny[l], uc, p.ny[l + 1]);
         else prolong_add<T, T>(U(l), p.nx[l], p.ny[l], U(l + 1), p.ny[l + 1]);
-        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.post);
+        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.post, p.iso1 != 0);
         if (l == 0) break;
         l -= 1;
       }
@@ -288,6 +294,7 @@ static int launch(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t 
   }
   if (off > 200 * 1024) return MG_ERR_UNSUPPORTED;
   p.nlev = nlev; p.cycle = cycle; p.pre = pre; p.post = post; p.u_zero = u_zero;
+  p.iso1 = (omega == 1.0 && hx == hy) ? 1 : 0;  // the same selection as mg_stream_api.cu
   p.ctol = ctol; p.cmaxit = cmaxit; p.u = (T*)u; p.f = (const T*)f; p.ld_u = ld_u; p.ld_f = ld_f; p.info = info;
   auto kern = small_cycle_kernel<T, TC>;
   static bool configured[64] = {false};

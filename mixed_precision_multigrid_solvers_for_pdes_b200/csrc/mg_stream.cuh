@@ -165,26 +165,32 @@ __device__ __forceinline__ void ldg2(const double* p, double& a, double& b) {
 }
 
 // Fast arithmetic (reciprocal multiplies + FMA); see the header comment for exactness.
+// Every rounding is pinned (explicit fma / non-contractible multiplies): were the scaling by 1/diag an ordinary
+// product, nvcc could fuse it into the add of a LATER stage that consumes the value -- in the unmasked fast path
+// but not behind the selects of the masked path -- and the last bit of a point would depend on which tile / slab
+// it falls in whenever 1/diag is not a power of two (Helmholtz shift, non-dyadic spacings).  Seen on 2 GPUs.
 template <typename T>
 __device__ __forceinline__ T relax_fast(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
-  const T nb = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
-  const T unew = (rhs + nb) * s.inv_neg_diag;
-  return fma(s.one_minus_omega, uc, s.omega * unew);
+  const T nb = fma(rt + lf, s.ihy2, Strict<T>::mul(up + dn, s.ihx2));
+  const T unew = Strict<T>::mul(rhs + nb, s.inv_neg_diag);
+  return fma(s.one_minus_omega, uc, Strict<T>::mul(s.omega, unew));
 }
 template <typename T>
 __device__ __forceinline__ T residual_fast(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
-  T t = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
+  T t = fma(rt + lf, s.ihy2, Strict<T>::mul(up + dn, s.ihx2));
   t = fma(-uc, s.cc, t);
   return fma(-s.shift, uc, fma(-s.coeff, t, f));  // exact no-op for shift = 0
 }
 
 // Isotropic (hx == hy), unrelaxed (omega == 1) specialisation: 5 instead of 8 instructions per point.
 // ((a+b)+(c+d))*ih2 equals (a+b)*ih2 + (c+d)*ih2 bit for bit when ih2 is a power of two (scaling by a power
-// of two commutes with rounding), and omega = 1 makes the relaxation blend the identity.
+// of two commutes with rounding), and omega = 1 makes the relaxation blend the identity: on dyadic grids without a
+// shift this is the reference's value.  Otherwise (Helmholtz shift, non-dyadic h) it is a slightly different --
+// equally accurate -- rounding of the same update, and like relax_fast it pins every rounding.
 template <typename T>
 __device__ __forceinline__ T relax_iso1(const StencilScalars<T>& s, T up, T dn, T rt, T lf, T rhs) {
   const T sum = (up + dn) + (rt + lf);
-  return fma(sum, s.ihx2, rhs) * s.inv_neg_diag;
+  return Strict<T>::mul(fma(sum, s.ihx2, rhs), s.inv_neg_diag);
 }
 template <typename T>
 __device__ __forceinline__ T residual_iso(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f) {
@@ -203,8 +209,8 @@ __device__ __forceinline__ T relax_sel(const StencilScalars<T>& s, T uc, T up, T
 template <bool SIMPLE, typename T>
 __device__ __forceinline__ T relax_jacobi(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs) {
   if (SIMPLE) return relax_iso1<T>(s, up, dn, rt, lf, rhs);
-  const T nb = fma(rt + lf, s.ihy2, (up + dn) * s.ihx2);
-  const T unew = (rhs + nb) * s.inv_neg_diag;
+  const T nb = fma(rt + lf, s.ihy2, Strict<T>::mul(up + dn, s.ihx2));
+  const T unew = Strict<T>::mul(rhs + nb, s.inv_neg_diag);
   return Strict<T>::add(Strict<T>::mul(s.one_minus_omega, uc), Strict<T>::mul(s.omega, unew));
 }
 template <bool SIMPLE, typename T>

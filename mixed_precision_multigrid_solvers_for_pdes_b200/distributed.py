@@ -632,18 +632,26 @@ class DistributedHeatSolver:
         y = domain[2] + np.arange(ny) * s.hy
         X, Y = np.meshgrid(x, y, indexing="ij")  # the slab's rows of Grid.X / Grid.Y (core/grid.py:50), ghosts included
 
+        def evaluate(fn, *args):
+            """User callback on the slab, ONE GRID ROW PER CALL: vectorised libm routines may round the same argument
+            differently depending on its position in the array, so evaluating whole slabs would make the last bit
+            of the data depend on the number of ranks; a (1, ny) row looks the same on every decomposition."""
+            out = np.empty(X.shape, dtype=np.float64)
+            for i in range(X.shape[0]):
+                out[i] = np.broadcast_to(np.asarray(fn(X[i:i + 1], Y[i:i + 1], *args), dtype=np.float64), (1, ny))[0]
+            return out
+
         def to_slab(a, like):
-            t = torch.from_numpy(np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), X.shape)))
-            return t.to(like.device)
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(like.device)
 
         def source(t):
             if problem.source_function is None:
                 return None
-            f = np.asarray(problem.source_function(X, Y, t), dtype=np.float64)
+            f = evaluate(problem.source_function, t)
             return f if f.any() else None
 
         b = eng.bufs(0, torch.float64)
-        b.u.copy_(to_slab(problem.initial_condition(X, Y), b.u))
+        b.u.copy_(to_slab(evaluate(problem.initial_condition), b.u))
         b.u[:, 0] = 0
         b.u[:, -1] = 0
         if s.own_lo == 0:
@@ -708,7 +716,7 @@ class DistributedHeatSolver:
             "halo_exchanges": sum(sv.eng.exchanges for sv in self._solvers.values()),
         }
         if problem.analytical_solution is not None:
-            exact = to_slab(problem.analytical_solution(X, Y, t_cur), u_loc)[lo:hi]
+            exact = to_slab(evaluate(problem.analytical_solution, t_cur), u_loc)[lo:hi]
             err = u_loc[lo:hi] - exact
             acc = torch.stack([(err ** 2).sum(), (exact ** 2).sum()]).to(torch.float64)
             eng.allreduce_sum(acc)
