@@ -51,10 +51,12 @@ def parse():
     ap.add_argument("--strategy", default="adaptive")
     ap.add_argument("--cycle", default="V")
     ap.add_argument("--loader", default="tma")
+    ap.add_argument("--smoother", default="rbgs", choices=["rbgs", "jacobi"],
+                    help="1-GPU arm: red-black GS (the BASELINE config) or damped Jacobi (omega = 2/3), both in the streaming kernel")
     ap.add_argument("--tolerance", type=float, default=None,
                     help="absolute h-scaled L2 residual tolerance; default 1e-8 (reference) up to 4097^2, 1e-7 above: "
                          "evaluating f - A u in fp64 has a rounding floor of ~eps*8/h^2*|u| = 3e-8 at h = 1/16384")
-    ap.add_argument("--cpu-n", type=int, default=4097, help="grid of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=8193, help="grid of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
     ap.add_argument("--strong", action="store_true",
@@ -224,6 +226,7 @@ def gpu_arm(a):
 
     solver = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
                                      cycle_type=a.cycle, loader=a.loader, max_iterations=10 ** 9, device=dev,
+                                     smoother=a.smoother,
                                      use_cuda_graphs=not a.no_graphs)
     solver.setup(n, n)
     eng, g = solver._engine, solver._grid
@@ -330,7 +333,8 @@ def gpu_arm(a):
     kernels = {}
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
         ach = alg_bytes(tag) / (d["mean_ms"] * 1e-3) / 1e9
-        sweeps = int(tag.split("rbgs")[1][0]) if "rbgs" in tag else 0
+        sm = "rbgs" if "rbgs" in tag else ("jac" if "jac" in tag else None)
+        sweeps = int(tag.split(sm)[1][0]) if sm else 0
         w = 8 if "/f64/" in tag else 4
         kernels[tag] = {"launches": d["launches"], "mean_ms": round(d["mean_ms"], 4), "hbm_gbs": round(ach, 1),
                         "frac_of_peak": round(ach / peak, 4), "share_of_step": round(d["total_ms"] / ms_eager, 4),
@@ -366,11 +370,29 @@ def gpu_arm(a):
             u_host, info = api.solve(prob)
             tot_t += time.perf_counter() - t0
             tot_c += info["iterations"]
-        e2e = {"value": n * n * tot_c / tot_t, "unit": UNIT, "h2d_bytes_per_step": n * n * 8,
-               "d2h_bytes_per_step": n * n * 8 + 8 * info["iterations"], "step": "one solve() call: pinned host f -> "
-               "device, %d cycles, device u -> pinned host" % info["iterations"], "seconds_per_solve": tot_t / reps,
-               "iterations": info["iterations"], "final_residual": info["final_residual"],
-               "max_error": float(ops.maxerr_sinsin(eng.levels[0].bufs(torch.float64).u))}
+        single = {"value": n * n * tot_c / tot_t, "seconds_per_solve": tot_t / reps}
+        # the batch API: B solves, each with its own H2D of f and D2H of u inside the timed region; transfers of
+        # neighbouring solves overlap the cycles (copy engines, side streams)
+        B = 6
+        outs = [torch.empty((n, n), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        probs = [prob] * B
+        api.solve_many(probs[:2], outputs=outs)  # warm-up: staging buffers, streams
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, infos = api.solve_many(probs, outputs=[outs[k % 2] for k in range(B)])
+        torch.cuda.synchronize()
+        tb = time.perf_counter() - t0
+        cyc = sum(i["iterations"] for i in infos)
+        info = infos[-1]
+        e2e = {"value": n * n * cyc / tb, "unit": UNIT, "h2d_bytes_per_step": n * n * 8,
+               "d2h_bytes_per_step": n * n * 8 + 8 * info["iterations"],
+               "step": "one solve of a solve_many() batch of %d: pinned host f -> device, %d cycles, device u -> pinned "
+                       "host; the transfers of neighbouring solves overlap the cycles" % (B, info["iterations"]),
+               "seconds_per_solve": tb / B, "iterations": info["iterations"], "final_residual": info["final_residual"],
+               "max_error": float(ops.maxerr_sinsin(eng.levels[0].bufs(torch.float64).u)),
+               "single_solve": {"value": single["value"], "seconds_per_solve": single["seconds_per_solve"],
+                                "step": "one solve() call, nothing overlapped: H2D of f, cycles, D2H of u back to back"}}
+        del outs
         del f_host
 
     cpu = None if a.no_cpu_baseline else run_cpu_baseline(a.cpu_n, 8)
@@ -381,7 +403,8 @@ def gpu_arm(a):
         "dtype": "f32 cycle / f64 iterate+residual" if solver.mode in ("switch", "refine") else
                  ("f64" if solver.mode == "fp64" else "f32"),
         "data": "synthetic",
-        "config": {"workload": f"2D Poisson {n}x{n} manufactured sin*sin, {a.cycle}(2,2) red-black GS, "
+        "config": {"workload": f"2D Poisson {n}x{n} manufactured sin*sin, {a.cycle}(2,2) "
+                               f"{'red-black GS' if a.smoother == 'rbgs' else 'damped Jacobi (2/3)'}, "
                                f"precision_strategy={a.strategy} (BASELINE configs[2])", "levels": eng.num_levels,
                    "loader": a.loader, "cuda_graphs": (not a.no_graphs), "graphs_captured": replayed, "priming_solves": primed,
                    "kernel_timing": "eager replay of the same %d steps with CUDA events around each level-0 launch "

@@ -129,6 +129,13 @@ MG_API int mg_sumsq(const void* x, int nx, int ny, int64_t ld, int dtype, double
              void* stream);
 MG_API int mg_sumsq_workspace_doubles(void);
 
+/* Host read-back of n (<= 1024) device doubles WITHOUT the copy engine: dst_host is page-locked host memory
+ * (cudaHostAlloc / torch pin_memory); a one-warp kernel stores the values through its device alias, so the read
+ * of a residual norm (the one scalar a cycle returns to the host, solvers/base.py:123-143) never queues behind a
+ * bulk device-to-host transfer running on another stream.  Asynchronous: synchronise `stream` before reading.
+ * Falls back to cudaMemcpyAsync when dst_host is not mapped page-locked memory. */
+MG_API int mg_read_doubles(const double* src, double* dst_host, int n, void* stream);
+
 /* dst = (dtype_dst) src, element-wise over (nx, ny)  (PrecisionManager.convert_array,
  * core/precision.py:106-134). */
 MG_API int mg_cast(const void* src, void* dst, int nx, int ny, int64_t ld_src, int64_t ld_dst,

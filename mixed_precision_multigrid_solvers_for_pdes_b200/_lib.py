@@ -24,6 +24,7 @@ SIGNATURES = {
     "mg_status_string": [_i],
     "mg_device_sm_count": [],
     "mg_launch_count": [],
+    "mg_read_doubles": [_p, _p, _i, _p],
     "mg_apply_laplacian": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _p],
     "mg_residual": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _i, _i, _p],
     "mg_smooth_rbgs": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _i, _i, _p],

@@ -320,6 +320,11 @@ __global__ void __launch_bounds__(RED_THREADS)
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
 
+// dst (mapped pinned host memory, addressed through its device alias) = src (device): a store over PCIe by the SMs
+__global__ void store_doubles_kernel(const double* __restrict__ src, double* __restrict__ dst, int n) {
+  for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
+}
+
 void reduce_partials_sum(const double* partials, int n, double* out, cudaStream_t st) {
   final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(partials, n, out);
 }
@@ -563,6 +568,20 @@ int mg_sumsq(const void* x, int nx, int ny, int64_t ld, int dtype, double* works
     sumsq_partial_kernel<float><<<blocks, RED_THREADS, 0, st>>>((const float*)x, nx, ny, ld, workspace);
   final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(workspace, blocks, out);
   return check_launch("mg_sumsq", 2);
+}
+
+int mg_read_doubles(const double* src, double* dst_host, int n, void* stream) {
+  MG_REQUIRE(src && dst_host && n >= 1 && n <= 1024);
+  cudaStream_t st = as_stream(stream);
+  void* alias = nullptr;
+  if (cudaHostGetDevicePointer(&alias, dst_host, 0) == cudaSuccess && alias != nullptr) {
+    store_doubles_kernel<<<1, 32, 0, st>>>(src, (double*)alias, n);
+    return check_launch("mg_read_doubles");
+  }
+  cudaGetLastError();  // not mapped pinned memory: the copy engine does it
+  return cudaMemcpyAsync(dst_host, src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st) == cudaSuccess
+             ? MG_OK
+             : MG_ERR_BADARG;
 }
 
 int mg_cast(const void* src, void* dst, int nx, int ny, int64_t ld_src, int64_t ld_dst, int dtype_src,

@@ -135,6 +135,22 @@ def sumsq_async(x: torch.Tensor, slot: int = 0) -> torch.Tensor:
     return out
 
 
+_host_slots: Dict[int, torch.Tensor] = {}
+
+
+def read_scalar(x: torch.Tensor) -> float:
+    """Value of a 1-element float64 device tensor on the host.  The value travels by a kernel store into page-locked
+    host memory (mg_read_doubles), not by the copy engine, so it cannot queue behind a bulk download that another
+    stream has in flight (MixedPrecisionMultigrid.solve_many); only the CURRENT stream is synchronised."""
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    h = _host_slots.get(dev)
+    if h is None:
+        h = _host_slots[dev] = torch.zeros(8, dtype=torch.float64, pin_memory=True)
+    _lib.call("mg_read_doubles", x.data_ptr(), h.data_ptr(), 1, stream_ptr())
+    torch.cuda.current_stream(x.device).synchronize()
+    return float(h[0])
+
+
 def sumsq(x: torch.Tensor) -> float:
     return float(sumsq_async(x).item())
 

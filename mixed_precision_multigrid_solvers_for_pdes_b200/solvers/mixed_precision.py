@@ -169,7 +169,7 @@ class MixedPrecisionMultigrid:
         return self._graph_cache.entries
 
     def _norm_from(self, ss: torch.Tensor) -> float:
-        return float(np.sqrt(self._grid.hx * self._grid.hy * ss.item()))
+        return float(np.sqrt(self._grid.hx * self._grid.hy * ops.read_scalar(ss)))
 
     # -- one cycle in each precision phase -----------------------------------------------------------------
     def _launch_uniform_cycle(self, dtype) -> None:
@@ -240,9 +240,7 @@ class MixedPrecisionMultigrid:
             eng.cycle(dtypes, l, None)
 
     # -- public API ------------------------------------------------------------------------------------------
-    def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None
-              ) -> Tuple[Any, Dict[str, Any]]:
-        t_start = time.perf_counter()
+    def _resolve_grid(self, problem, nx, ny):
         nx = nx or getattr(problem, "nx", None)
         ny = ny or getattr(problem, "ny", None) or nx
         rhs = getattr(problem, "rhs_array", None)
@@ -253,33 +251,41 @@ class MixedPrecisionMultigrid:
         domain = tuple(getattr(problem, "domain", (0.0, 1.0, 0.0, 1.0)))
         if self._engine is None or self._shape != (nx, ny) or self._domain != domain:
             self.setup(nx, ny, domain)
+        return nx, ny, domain, rhs
+
+    def _load_rhs(self, problem, rhs, domain, dst: torch.Tensor) -> bool:
+        """Right-hand side of `problem` into the pitched fp64 device field `dst` (on the current stream).
+        Returns True when the caller handed in host data (host in -> host out)."""
         eng, g = self._engine, self._grid
-        b64 = eng.levels[0].bufs(torch.float64)
         was_np = True
-        # right-hand side into the fp64 level-0 buffer
         if rhs is not None:
-            was_np = not (isinstance(rhs, torch.Tensor) and rhs.is_cuda)  # host in -> host out
+            was_np = not (isinstance(rhs, torch.Tensor) and rhs.is_cuda)
             if isinstance(rhs, torch.Tensor):
-                b64.f.copy_(rhs, non_blocking=True)  # pinned host tensors upload asynchronously
+                dst.copy_(rhs, non_blocking=True)  # pinned host tensors upload asynchronously
             else:
-                b64.f.copy_(to_device(rhs, device=eng.dev)[0])
+                dst.copy_(to_device(rhs, device=eng.dev)[0])
         elif getattr(problem, "device_mms", None) is not None:
             amp, kx, ky = problem.device_mms
-            ops.fill_sinsin_(b64.f, domain, amp, kx, ky)
+            ops.fill_sinsin_(dst, domain, amp, kx, ky)
         else:
             f_host = np.asarray(problem.source_function(g.X, g.Y), dtype=np.float64)
-            b64.f.copy_(to_device(f_host, device=eng.dev)[0])
-        if not self.strict_reference_norm:
-            b64.f[0, :] = 0
-            b64.f[-1, :] = 0
-            b64.f[:, 0] = 0
-            b64.f[:, -1] = 0
-        if initial_guess is None:
-            b64.u.zero_()
-        else:
-            b64.u.copy_(to_device(initial_guess, device=eng.dev, dtype=torch.float64)[0])
-        t_setup = time.perf_counter() - t_start
+            dst.copy_(to_device(f_host, device=eng.dev)[0])
+        return was_np
 
+    def _zero_ring(self, f: torch.Tensor) -> None:
+        if not self.strict_reference_norm:
+            f[0, :] = 0
+            f[-1, :] = 0
+            f[:, 0] = 0
+            f[:, -1] = 0
+
+    def _solve_device(self, have_guess: bool):
+        """The cycle loop on the right-hand side / iterate already in the fp64 level-0 buffers.  Synchronises only
+        the current stream (never the device), so copies on other streams keep flowing.
+        Returns (device solution, partial info)."""
+        eng = self._engine
+        b64 = eng.levels[0].bufs(torch.float64)
+        cur = torch.cuda.current_stream(eng.dev)
         history: List[float] = []
         precisions: List[str] = []
         self.precision_switches = []
@@ -290,9 +296,9 @@ class MixedPrecisionMultigrid:
             ops.cast(b64.u, torch.float32, out=b32.u)
         converged = False
         iteration = 0
-        torch.cuda.synchronize(eng.dev)
+        cur.synchronize()
         t_cycles = time.perf_counter()
-        if self.fmg and initial_guess is None:
+        if self.fmg and not have_guess:
             if phase == "refine":  # fp32 FMG on the rounded right-hand side, result promoted to the fp64 iterate
                 b32 = eng.levels[0].bufs(torch.float32)
                 ops.cast(b64.f, torch.float32, out=b32.f)
@@ -326,41 +332,139 @@ class MixedPrecisionMultigrid:
                                                     "to": "float64",
                                                     "reason": "stagnation" if stagnating else "switch_threshold"})
                     phase = "fp64"
-        torch.cuda.synchronize(eng.dev)
+        cur.synchronize()
         t_solve = time.perf_counter() - t_cycles
-
+        b64 = eng.levels[0].bufs(torch.float64)
         if phase == "fp32":
-            b32 = eng.levels[0].bufs(torch.float32)
-            u_dev = ops.cast(b32.u, torch.float64, out=b64.tmp)
+            u_dev = ops.cast(eng.levels[0].bufs(torch.float32).u, torch.float64, out=b64.tmp)
         else:
-            u_dev = eng.levels[0].bufs(torch.float64).u
-        if was_np:
-            # device -> pinned host staging (kept across solves; the returned array is a view of it and is
-            # overwritten by the next solve of this solver object)
-            if self._pinned_out is None or tuple(self._pinned_out.shape) != (nx, ny):
-                self._pinned_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True)
-            self._pinned_out.copy_(u_dev, non_blocking=True)
-            torch.cuda.synchronize(eng.dev)
-            solution = self._pinned_out.numpy()
-        else:
-            solution = u_dev.clone()
-        total = time.perf_counter() - t_start
+            u_dev = b64.u
+        nx, ny = self._shape
         ratios = [history[k] / history[k - 1] for k in range(max(1, len(history) - 4), len(history))
                   if history[k - 1] > 0 and 0 < history[k] / history[k - 1] < 1]
         info = {
             "converged": converged, "iterations": iteration, "final_residual": history[-1] if history else pending,
             "residual": history[-1] if history else pending, "residual_history": history,
             "initial_residual": pending, "convergence_rate": float(np.mean(ratios)) if ratios else 0.0,
-            "solve_time": total, "cycle_time": t_solve, "setup_time": t_setup, "total_time": total,
-            "average_time_per_iteration": t_solve / max(1, iteration), "precision_history": precisions,
-            "precision_levels_used": sorted(set(precisions)), "precision_switches": list(self.precision_switches),
-            "precision_strategy": self.precision_strategy, "switch_threshold": self.switch_threshold, "fmg": self.fmg,
-            "cycle_type": self.cycle_type, "num_levels": eng.num_levels,
-            "grid_hierarchy": [(l.grid.nx, l.grid.ny) for l in eng.levels], "level_timings": {},
-            "pre_smooth_iterations": self.pre, "post_smooth_iterations": self.post,
+            "cycle_time": t_solve, "average_time_per_iteration": t_solve / max(1, iteration),
+            "precision_history": precisions, "precision_levels_used": sorted(set(precisions)),
+            "precision_switches": list(self.precision_switches), "precision_strategy": self.precision_strategy,
+            "switch_threshold": self.switch_threshold, "fmg": self.fmg, "cycle_type": self.cycle_type,
+            "num_levels": eng.num_levels, "grid_hierarchy": [(l.grid.nx, l.grid.ny) for l in eng.levels],
+            "level_timings": {}, "pre_smooth_iterations": self.pre, "post_smooth_iterations": self.post,
             "unknowns_per_second": nx * ny * iteration / t_solve if t_solve > 0 else 0.0,
         }
+        return u_dev, info
+
+    def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None
+              ) -> Tuple[Any, Dict[str, Any]]:
+        t_start = time.perf_counter()
+        nx, ny, domain, rhs = self._resolve_grid(problem, nx, ny)
+        eng = self._engine
+        b64 = eng.levels[0].bufs(torch.float64)
+        was_np = self._load_rhs(problem, rhs, domain, b64.f)
+        self._zero_ring(b64.f)
+        if initial_guess is None:
+            b64.u.zero_()
+        else:
+            b64.u.copy_(to_device(initial_guess, device=eng.dev, dtype=torch.float64)[0])
+        t_setup = time.perf_counter() - t_start
+        u_dev, info = self._solve_device(initial_guess is not None)
+        if was_np:
+            # device -> pinned host staging (kept across solves; the returned array is a view of it and is
+            # overwritten by the next solve of this solver object)
+            if self._pinned_out is None or tuple(self._pinned_out.shape) != (nx, ny):
+                self._pinned_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True)
+            self._pinned_out.copy_(u_dev, non_blocking=True)
+            torch.cuda.current_stream(eng.dev).synchronize()
+            solution = self._pinned_out.numpy()
+        else:
+            solution = u_dev.clone()
+        total = time.perf_counter() - t_start
+        info.update({"solve_time": total, "setup_time": t_setup, "total_time": total})
         return solution, info
+
+    def solve_many(self, problems, outputs=None) -> Tuple[List[Any], List[Dict[str, Any]]]:
+        """A batch of solves on ONE grid (many right-hand sides: time steps, parameter sweeps), software-pipelined
+        over the copy engines: while solve k cycles, the right-hand side of solve k+1 is uploaded on its own stream
+        and the solution of solve k-1 is downloaded on another, so a batch is bound by max(H2D, cycles, D2H) per
+        solve instead of their sum (PCIe moves 2 x 8 bytes per unknown; a 16385^2 solve is ~27 ms of cycles between
+        two ~40 ms transfers).  `problems`: PoissonProblem objects (or anything `solve` accepts) sharing grid size and
+        domain; right-hand sides given as PINNED host tensors upload asynchronously.  `outputs`: optional list of
+        host tensors (pinned for overlap) receiving the solutions; allocated pinned when omitted.  Each solve starts
+        from u = 0 and is bit-identical to `solve(problem)`.  Returns ([solutions as NumPy views], [info])."""
+        problems = list(problems)
+        if not problems:
+            return [], []
+        t_start = time.perf_counter()
+        nx, ny, domain, _ = self._resolve_grid(problems[0], None, None)
+        eng = self._engine
+        dev = eng.dev
+        n = len(problems)
+        if outputs is None:
+            outputs = [torch.empty((nx, ny), dtype=torch.float64, pin_memory=True) for _ in range(n)]
+        elif len(outputs) != n or any(tuple(o.shape) != (nx, ny) or o.dtype != torch.float64 for o in outputs):
+            raise ValueError("solve_many: `outputs` must be one float64 (nx, ny) host tensor per problem")
+        if getattr(self, "_stage", None) is None or self._stage[0][0].shape != (nx, ny):
+            self._stage = ([empty_field(nx, ny, torch.float64, dev) for _ in range(2)],   # right-hand sides
+                           [empty_field(nx, ny, torch.float64, dev) for _ in range(2)],   # solutions
+                           torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        f_stage, u_stage, s_in, s_out = self._stage
+        cur = torch.cuda.current_stream(dev)
+        consumed = [None, None]   # event: the compute stream has copied f_stage[slot] into the engine
+        drained = [None, None]    # event: u_stage[slot] has reached the host
+        uploaded: List[Any] = [None] * n
+
+        def upload(k):
+            slot = k % 2
+            pk = problems[k]
+            kx, ky, kd, rhs = (getattr(pk, "nx", None) or nx, getattr(pk, "ny", None) or ny,
+                               tuple(getattr(pk, "domain", domain)), getattr(pk, "rhs_array", None))
+            if (kx, ky) != (nx, ny) or tuple(kd) != tuple(domain):
+                raise ValueError("solve_many: every problem must share the grid size and domain of the first")
+            with torch.cuda.stream(s_in):
+                if consumed[slot] is not None:
+                    s_in.wait_event(consumed[slot])
+                self._load_rhs(pk, rhs, domain, f_stage[slot])
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+            uploaded[k] = ev
+
+        upload(0)
+        infos = []
+        for k in range(n):
+            slot = k % 2
+            if k + 1 < n:
+                upload(k + 1)
+            t0 = time.perf_counter()
+            b64 = eng.levels[0].bufs(torch.float64)
+            cur.wait_event(uploaded[k])
+            b64.f.copy_(f_stage[slot])
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            consumed[slot] = ev
+            self._zero_ring(b64.f)
+            b64.u.zero_()
+            u_dev, info = self._solve_device(False)
+            if drained[slot] is not None:
+                cur.wait_event(drained[slot])
+            u_stage[slot].copy_(u_dev)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ready)
+                outputs[k].copy_(u_stage[slot], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_out)
+            drained[slot] = ev
+            info.update({"solve_time": time.perf_counter() - t0, "setup_time": 0.0})
+            infos.append(info)
+        s_out.synchronize()
+        total = time.perf_counter() - t_start
+        for info in infos:
+            info["total_time"] = total / n
+            info["batch_time"] = total
+        return [o.numpy() for o in outputs], infos
 
 
 # doc-only aliases seen in the reference notebooks (SURVEY 8b)

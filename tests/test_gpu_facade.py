@@ -130,3 +130,38 @@ def test_full_multigrid_start_saves_cycles(strategy):
         assert abs(np.max(np.abs(u - O.mms_exact(n))) - ref) <= 0.01 * ref
     # the FMG iterate alone is already at discretisation-error level: first residual far below the zero-start one
     assert i1["residual_history"][0] < 0.05 * i0["residual_history"][0]
+
+
+@pytest.mark.parametrize("strategy", ["adaptive", "double"])
+def test_solve_many_pipelines_transfers_and_equals_sequential_solves(strategy):
+    """solve_many: uploads / downloads of neighbouring solves overlap the cycles on side streams; every solution and
+    residual history must equal the plain solve() of the same right-hand side bit for bit (5 solves > 2 staging slots)."""
+    n = 257
+    rng = np.random.default_rng(5)
+    x = np.linspace(0, 1, n)
+    X, Y = np.meshgrid(x, x, indexing="ij")
+    rhs = [(k + 1) * np.sin((k + 1) * np.pi * X) * np.sin(np.pi * Y) + 0.1 * rng.standard_normal((n, n)) for k in range(5)]
+    solver = MixedPrecisionMultigrid(precision_strategy=strategy, tolerance=1e-8)
+    seq = []
+    for f in rhs:
+        u, info = solver.solve(PoissonProblem(rhs=f, nx=n, ny=n))
+        seq.append((u.copy(), info["residual_history"]))
+    pinned = []
+    for f in rhs:
+        t = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
+        t.copy_(torch.from_numpy(f))
+        pinned.append(PoissonProblem(rhs=t, nx=n, ny=n))
+    for probs in (pinned, [PoissonProblem(rhs=f, nx=n, ny=n) for f in rhs]):  # pinned tensors, then plain NumPy
+        sols, infos = solver.solve_many(probs)
+        assert len(sols) == len(infos) == 5
+        for (u, hist), u2, info in zip(seq, sols, infos):
+            assert info["converged"] and info["residual_history"] == hist
+            assert np.array_equal(u, u2)
+    outs = [torch.empty((n, n), dtype=torch.float64, pin_memory=True) for _ in range(2)]
+    sols, _ = solver.solve_many(pinned[:2], outputs=outs)
+    assert np.array_equal(sols[1], seq[1][0]) and sols[1].ctypes.data == outs[1].numpy().ctypes.data
+    with pytest.raises(ValueError, match="outputs"):
+        solver.solve_many(pinned[:2], outputs=outs[:1])
+    with pytest.raises(ValueError, match="share the grid"):
+        solver.solve_many([pinned[0], PoissonProblem(rhs=np.zeros((129, 129)), nx=129, ny=129)])
+    assert solver.solve_many([]) == ([], [])

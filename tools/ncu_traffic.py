@@ -9,7 +9,7 @@ import sys
 rep, n, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
 order = sys.argv[4].split(",")  # e.g. "f32:zdown2,f32:up2,f64:defect"
 TAGS = {"smooth2": "rbgs2", "zdown2": "Z+rbgs2+R", "down2": "rbgs2+R", "up2": "P+rbgs2", "up2norm": "P+rbgs2+N",
-        "defect": "update+resid32+N"}
+        "defect": "update+resid32+N", "jac2": "jac2", "jacdown2": "jac2+R", "jacup2": "P+jac2"}
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, data = rows[0], rows[1], rows[2:]
