@@ -130,14 +130,27 @@ template <typename T> struct Row4 { T v[4]; };
 struct TrueTag { static constexpr bool value = true; };
 struct FalseTag { static constexpr bool value = false; };
 
-__device__ __forceinline__ void lds4(const float* p, float (&v)[4]) {
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+// Shared-memory reads take 32-bit shared-window addresses: through generic pointers the compiler rebuilt the window
+// base (S2UR SR_CgaCtaId / ULEA chains) at every group of loads, ~14 % of the stall samples of the fp32 down pass (ncu r01).
+__device__ __forceinline__ void lds4(uint32_t a, float (&v)[4]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
 }
-__device__ __forceinline__ void lds4(const double* p, double (&v)[4]) {
-  const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
-  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+__device__ __forceinline__ void lds4(uint32_t a, double (&v)[4]) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + 16u));
 }
+__device__ __forceinline__ void lds2(uint32_t a, float& x, float& y) {
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(x), "=f"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds2(uint32_t a, double& x, double& y) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+}
+__device__ __forceinline__ void lds1(uint32_t a, float& x) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a)); }
+__device__ __forceinline__ void lds1(uint32_t a, double& x) { asm volatile("ld.shared.f64 %0, [%1];" : "=d"(x) : "r"(a)); }
+
+// Global stores predicated per lane, never branched: which lanes own which of their 4 columns differs along the warp
+// (strip halos), and `if (own == ...) store` chains compiled to BSSY / jump table / BRX / BSYNC around every row
+// (branch_resolving was the second largest stall of the fp32 down pass, ncu r01).
 __device__ __forceinline__ void stg4(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
@@ -145,16 +158,36 @@ __device__ __forceinline__ void stg4(double* p, const double (&v)[4]) {
   *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
   *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
 }
+__device__ __forceinline__ void stg4_if(bool on, float* p, float a, float b, float c, float d) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}" ::"r"((int)on),
+               "l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+__device__ __forceinline__ void stg4_if(bool on, double* p, double a, double b, double c, double d) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v2.f64 [%1], {%2, %3};\n\t@q st.global.v2.f64 [%1+16], {%4, %5};\n\t}" ::"r"(
+          (int)on),
+      "l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+      : "memory");
+}
+__device__ __forceinline__ void stg2_if(bool on, float* p, float a, float b) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v2.f32 [%1], {%2, %3};\n\t}" ::"r"((int)on), "l"(p), "f"(a),
+               "f"(b)
+               : "memory");
+}
+__device__ __forceinline__ void stg2_if(bool on, double* p, double a, double b) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v2.f64 [%1], {%2, %3};\n\t}" ::"r"((int)on), "l"(p), "d"(a),
+               "d"(b)
+               : "memory");
+}
+__device__ __forceinline__ void stg1_if(bool on, float* p, float a) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.f32 [%1], %2;\n\t}" ::"r"((int)on), "l"(p), "f"(a) : "memory");
+}
+__device__ __forceinline__ void stg1_if(bool on, double* p, double a) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.f64 [%1], %2;\n\t}" ::"r"((int)on), "l"(p), "d"(a) : "memory");
+}
 __device__ __forceinline__ void stg2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void stg2(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
-__device__ __forceinline__ void lds2(const float* p, float& a, float& b) {
-  const float2 t = *reinterpret_cast<const float2*>(p);
-  a = t.x; b = t.y;
-}
-__device__ __forceinline__ void lds2(const double* p, double& a, double& b) {
-  const double2 t = *reinterpret_cast<const double2*>(p);
-  a = t.x; b = t.y;
-}
 __device__ __forceinline__ void ldg2(const float* p, float& a, float& b) {
   const float2 t = __ldg(reinterpret_cast<const float2*>(p));
   a = t.x; b = t.y;
@@ -251,6 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strip = blockIdx.x * WARPS + warp;
   unsigned char* ring = smem + (size_t)warp * NSTAGE * STAGE_BYTES;  // [stage][u box | f box | e box]
+  const uint32_t ring_a = smem_u32(ring);                            // the same, as a shared-window address
 
   if (LOADER == LOADER_TMA) {
     if (lane == 0) {
@@ -289,6 +323,8 @@ __global__ void __launch_bounds__(WARPS * 32)
     dom |= d ? (1u << e) : 0u;
     own |= o ? (1u << e) : 0u;
   }
+
+  const bool own_all = own == 0xFu, own_lo = own == 0x3u, own_hi = own == 0xCu;  // per-lane constants
 
   // ---- loader ----------------------------------------------------------------------------------
   auto issue_box = [&](int box) {
@@ -400,10 +436,11 @@ __global__ void __launch_bounds__(WARPS * 32)
     load_coarse_row((i_begin >> 1) + 1, c1, true);
   }
   // staged variant: row `rel` (0 .. RB/2) of the current box's coarse slab, columns 2*lane .. 2*lane + 2
-  auto read_coarse_row = [&](const T* sc_box, int rel, T(&c)[3]) {
-    const T* row = sc_box + rel * COARSE_BOX_W + ((g0 >> 1) & CALIGN) + 2 * lane;
+  const uint32_t coarse_lane_off = (uint32_t)((((g0 >> 1) & CALIGN) + 2 * lane) * (int)sizeof(T));
+  auto read_coarse_row = [&](uint32_t sc_box, int rel, T(&c)[3]) {
+    const uint32_t row = sc_box + (uint32_t)(rel * COARSE_BOX_W * (int)sizeof(T)) + coarse_lane_off;
     lds2(row, c[0], c[1]);
-    c[2] = row[2];
+    lds1(row + 2u * (uint32_t)sizeof(T), c[2]);
   };
 
   T* const uout = reinterpret_cast<T*>(p.u_out);
@@ -412,9 +449,11 @@ __global__ void __launch_bounds__(WARPS * 32)
 
   // ---- one box of RB rows.  MASKED = false is the interior fast path: every row and column the box
   //      touches is an interior point, so there are no boundary tests, selects or divergent branches. ----
-  auto process_box = [&](auto masked_tag, const int ib, const T* su, const T* sf, const float* se) {
+  // su / sf / se: shared-window addresses of this lane's 4 elements of the box's first u / f / fp32-correction row;
+  // sc_box: of the box's coarse slab (STAGE_COARSE)
+  auto process_box = [&](auto masked_tag, const int ib, const uint32_t su, const uint32_t sf, const uint32_t se,
+                         const uint32_t sc_box) {
     constexpr bool MASKED = decltype(masked_tag)::value;
-    const T* sc_box = reinterpret_cast<const T*>(se - lane * LANE_V);  // coarse slab of this box (STAGE_COARSE)
     if (STAGE_COARSE) {
       read_coarse_row(sc_box, 0, c0);
       read_coarse_row(sc_box, 1, c1);
@@ -442,14 +481,15 @@ __global__ void __launch_bounds__(WARPS * 32)
 #pragma unroll
         for (int e = 0; e < 4; ++e) w[0][e] = (T)0;
       } else {
-        lds4(su + k * STRIP, w[0]);
+        lds4(su + (uint32_t)(k * STRIP * (int)sizeof(T)), w[0]);
       }
-      lds4(sf + k * STRIP, fr[0]);
+      lds4(sf + (uint32_t)(k * STRIP * (int)sizeof(T)), fr[0]);
 
       // (1a) FRONT_ADDFINE: u += (T)e  (rows/columns outside the domain hold zeros in both arrays)
       if (FRONT == FRONT_ADDFINE) {
-        const float4 ev = *reinterpret_cast<const float4*>(se + k * STRIP);
-        w[0][0] += (T)ev.x; w[0][1] += (T)ev.y; w[0][2] += (T)ev.z; w[0][3] += (T)ev.w;
+        float ev[4];
+        lds4(se + (uint32_t)(k * STRIP * 4), ev);
+        w[0][0] += (T)ev[0]; w[0][1] += (T)ev[1]; w[0][2] += (T)ev[2]; w[0][3] += (T)ev[3];
       }
 
       // (1b) FRONT_PROLONG: u += bilinear prolongation of the coarse correction (transfer.py:234-267 semantics)
@@ -531,10 +571,10 @@ __global__ void __launch_bounds__(WARPS * 32)
         const bool row_ok = store_u && (rows_owned || (qf >= I0 && qf < I1));
         T* dst = orow;
         orow += p.ld_out;
-        if (!MASKED) {  // interior strip: ownership changes only at even columns
-          if (row_ok && own == 0xFu) stg4(dst, w[NS]);
-          if (row_ok && own == 0x3u) stg2(dst, w[NS][0], w[NS][1]);
-          if (row_ok && own == 0xCu) stg2(dst + 2, w[NS][2], w[NS][3]);
+        if (!MASKED) {  // interior strip: ownership changes only at even columns; three predicated stores, no branch
+          stg4_if(row_ok && own_all, dst, w[NS][0], w[NS][1], w[NS][2], w[NS][3]);
+          stg2_if(row_ok && own_lo, dst, w[NS][0], w[NS][1]);
+          stg2_if(row_ok && own_hi, dst + 2, w[NS][2], w[NS][3]);
         } else if (row_ok && own != 0u) {
           if (own == 0xFu) {
             stg4(dst, w[NS]);
@@ -624,12 +664,9 @@ __global__ void __launch_bounds__(WARPS * 32)
               }
               const bool o0 = (own & 1u) != 0u, o1 = (own & 4u) != 0u;
               T* dst = cout + (int64_t)ic * p.ld_co + jc0;
-              if (o0 && o1) {
-                stg2(dst, v0, v1);
-              } else {
-                if (o0) dst[0] = v0;
-                if (o1) dst[1] = v1;
-              }
+              stg2_if(o0 && o1, dst, v0, v1);
+              stg1_if(o0 && !o1, dst, v0);
+              stg1_if(o1 && !o0, dst + 1, v1);
             }
           }
         }
@@ -646,17 +683,19 @@ __global__ void __launch_bounds__(WARPS * 32)
       cp_async_wait<NSTAGE - 1>();
       __syncwarp();
     }
-    const T* su = reinterpret_cast<const T*>(ring + (size_t)stage * STAGE_BYTES) + lane * LANE_V;
-    const T* sf = su + RB * STRIP;
-    const float* se = reinterpret_cast<const float*>(ring + (size_t)stage * STAGE_BYTES + 2 * BOX_BYTES) + lane * LANE_V;
+    const uint32_t sbox = ring_a + (uint32_t)stage * STAGE_BYTES;
+    const uint32_t su = sbox + (uint32_t)(lane * LANE_V * (int)sizeof(T));
+    const uint32_t sf = su + BOX_BYTES;
+    const uint32_t sc_box = sbox + 2 * BOX_BYTES;              // coarse slab (STAGE_COARSE) ...
+    const uint32_t se = sc_box + (uint32_t)(lane * LANE_V * 4);  // ... or fp32 correction rows (FRONT_ADDFINE)
     const int ib = i_begin + box * RB;
     // interior fast path: every row evaluated in this box (oldest: ib - NS - 1 with a BACK stage) and the
     // newest row ib + RB - 1 are interior rows, and the strip has no boundary column
     // (with restriction also the centre row q2 - 1 of the oldest coarse row, hence 3 instead of 1)
     constexpr int OLDEST = NS + (BACK == BACK_RESTRICT ? 3 : (HAS_BACK ? 1 : 0));
     const bool fast = strip_interior && (ib - OLDEST >= 1) && (ib + RB - 1 <= nx - 2);
-    if (fast) process_box(FalseTag{}, ib, su, sf, se);
-    else process_box(TrueTag{}, ib, su, sf, se);
+    if (fast) process_box(FalseTag{}, ib, su, sf, se, sc_box);
+    else process_box(TrueTag{}, ib, su, sf, se, sc_box);
 
     // refill this stage with box + NSTAGE
     __syncwarp();
