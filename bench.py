@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--cpu-n", type=int, default=8193, help="grid of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
+    ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
+                    help="multi-GPU ghost exchange: grouped NCCL send/recv (default) or one-sided pushes over NVLink peer "
+                         "memory (halo.py; opt-in until measured)")
     ap.add_argument("--strong", action="store_true",
                     help="multi-GPU: --n is the GLOBAL grid (n x n on the unit square) split into row slabs")
     ap.add_argument("--no-e2e", action="store_true")

@@ -204,7 +204,7 @@ class DistributedCycleEngine:
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), num_levels: Optional[int] = None,
                  cycle_type: str = "V", pre: int = 2, post: int = 2, agglomerate_below: int = 1025,
                  dist_levels: Optional[int] = None, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
-                 shift: float = 0.0, backend=None, group=None, device=None):
+                 shift: float = 0.0, backend=None, group=None, device=None, transport=None):
         if not (1 <= pre <= 2 and 1 <= post <= 2):
             raise ValueError("the distributed engine runs 1 or 2 pre/post sweeps per pass")
         if not shift >= 0.0:
@@ -227,6 +227,9 @@ class DistributedCycleEngine:
         self.part = SlabPartition(nx, ny, self.world, self.rank, num_levels, max(1, dist_levels), domain)
         self.D = self.part.dist_levels
         self.be = backend if backend is not None else DeviceBackend(device)
+        # optional one-sided halo transport (halo.py): slab arrays in symmetric memory, ghost rows pushed into the
+        # neighbours over peer mappings instead of NCCL send/recv.  None = the NCCL exchange below.
+        self.transport = transport
         self._bufs: Dict[Tuple[int, torch.dtype], _Bufs] = {}
         self.valid: Dict[int, int] = {}  # data_ptr -> number of ghost rows per side that currently hold exact values
         an, am = self.part.agg_shape
@@ -264,7 +267,11 @@ class DistributedCycleEngine:
         if b is None:
             s = self.part.slab(l)
             b = _Bufs()
-            b.u, b.tmp, b.f = (self.be.empty(s.loc_nx, s.ny, dtype) for _ in range(3))
+            if self.transport is not None:  # collective: every rank creates its buffers in the same order
+                rows_max = (s.nx_glob - 1) // self.world + 2 * self.part.ghost + 1
+                b.u, b.tmp, b.f = (self.transport.alloc(s.loc_nx, rows_max, s.ny, dtype) for _ in range(3))
+            else:
+                b.u, b.tmp, b.f = (self.be.empty(s.loc_nx, s.ny, dtype) for _ in range(3))
             self._bufs[key] = b
         return b
 
@@ -278,6 +285,10 @@ class DistributedCycleEngine:
         for t, l in items:
             self.valid[t.data_ptr()] = self.part.ghost
         if self.world == 1 or not items:
+            return
+        if self.transport is not None:
+            self.transport.exchange(self.part, items)
+            self.exchanges += 1
             return
         G = self.part.ghost
         ops_, fix = [], []
@@ -750,7 +761,8 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
                                           device=dev, use_cuda_graphs=not a.no_graphs,
-                                          **({"agglomerate_below": a.agg} if getattr(a, "agg", None) else {}))
+                                          **({"agglomerate_below": a.agg} if getattr(a, "agg", None) else {}),
+                                          **_halo_kw(a, dev))
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
     sol.eng.exchange(sol.eng.bufs(0, torch.float64).f, 0)
@@ -860,13 +872,21 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                                f"{a.cycle}(2,2) red-black GS, precision_strategy={a.strategy}, row slabs over {world} GPUs",
                    "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": GHOST,
                    "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
-                   "halo_exchanges_per_step": ex_per_step, "cuda_graphs": (not a.no_graphs),
+                   "halo_exchanges_per_step": ex_per_step, "halo": getattr(a, "halo", "nccl"),
+                   "cuda_graphs": (not a.no_graphs),
                    "graphs_captured": sol.graphs.captured, "priming_solves": primed,
                    "l2": "slab arrays (>= 1 GB) exceed the 126 MB L2; no flush needed",
                    "cycles_per_solve": state["cycles"][-3:], "last_residual_history": state["last"]},
         "roofline": roof, "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
     }
+
+
+def _halo_kw(a, dev) -> Dict[str, Any]:
+    if getattr(a, "halo", "nccl") != "p2p":
+        return {}
+    from .halo import SymmMemTransport
+    return {"transport": SymmMemTransport(dev, GHOST)}
 
 
 def _metric_name() -> str:

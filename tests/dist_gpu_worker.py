@@ -24,10 +24,16 @@ def main():
     import time
     res = {}
     t00 = time.time()
+    p2p = os.environ.get("MGB200_TEST_HALO") == "p2p"  # ghost rows pushed over peer memory (halo.py) instead of NCCL
     for strategy in ("double", "adaptive", "adaptive_graphs"):
+        kw = {}
+        if p2p:
+            from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import GHOST
+            from mixed_precision_multigrid_solvers_for_pdes_b200.halo import SymmMemTransport
+            kw["transport"] = SymmMemTransport(dev, GHOST)
         sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy.split("_")[0],
                                               tolerance=1e-8, agglomerate_below=129, device=dev,
-                                              use_cuda_graphs=strategy.endswith("graphs"))
+                                              use_cuda_graphs=strategy.endswith("graphs"), **kw)
         sol.set_rhs_from_global(torch.from_numpy(f).to(dev))
         print(f"[worker r{dist.get_rank()}] {strategy}: start solve at {time.time() - t00:.1f}s D={sol.eng.D}", file=sys.stderr, flush=True)
         u, info = sol.solve()
@@ -44,6 +50,17 @@ def main():
                          "u": full.cpu().numpy()}
         res["exchanges"] = info["halo_exchanges"]
         res["D"] = sol.eng.D
+    if p2p:
+        res["pushes"] = kw["transport"].pushes
+        if dist.get_rank() == 0:
+            torch.save(res, sys.argv[1])
+        del sol, u, full, kw
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     # BASELINE configs[4] on slabs: 3 backward-Euler steps + a shortened 4th, one shifted solve per step, graphs on
     from mixed_precision_multigrid_solvers_for_pdes_b200 import HeatProblem, TimeSteppingConfig, TimeSteppingMethod
     from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
