@@ -466,6 +466,12 @@ class MixedPrecisionMultigrid:
             info["batch_time"] = total
         return [o.numpy() for o in outputs], infos
 
+    def release_staging(self) -> None:
+        """Free the double-buffered device staging fields and side streams `solve_many` keeps between calls
+        (4 fields of the grid size: 8.6 GB at 16385^2)."""
+        self._stage = None
+        self._pinned_out = None
+
 
 # doc-only aliases seen in the reference notebooks (SURVEY 8b)
 MixedPrecisionMultigridSolver = MixedPrecisionMultigrid
