@@ -160,3 +160,23 @@ def test_c_oracle_large_grid_matches_numpy_oracle():
     ua, ia = a.solve(f)
     ub, ib = b.solve(f)
     assert np.array_equal(ua, ub) and ia["residual_history"] == ib["residual_history"]
+
+
+def test_corrected_multigrid_oracle_matches_reference_runs():
+    """oracle/corrected_oracle.py (the reference's SECONDARY solver, corrected_multigrid.py) against runs of the reference's
+    own class: hierarchies, cycle counts, residual histories and solutions, bit for bit."""
+    import json
+    import os
+
+    from oracle import corrected_oracle as CM
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "corrected_golden.npz"))
+    meta = json.loads(str(g["meta"]))
+    assert meta["cases"]
+    for c in meta["cases"]:
+        s = CM.OracleCorrectedMultigrid(max_levels=c["levels"], max_iterations=c["max_iterations"], tolerance=c["tolerance"])
+        rhs = g[c["name"] + "_rhs"]
+        r = s.solve(np.zeros_like(rhs), rhs)
+        assert [list(x) for x in s.shapes] == c["hierarchy"], c["name"]
+        assert r["iterations"] == c["iterations"] and r["converged"] == c["converged"], c["name"]
+        assert np.array_equal(np.array(r["residual_history"]), g[c["name"] + "_hist"]), c["name"]
+        assert np.array_equal(r["solution"], g[c["name"] + "_u"]), c["name"]
