@@ -54,9 +54,12 @@ def parse():
     ap.add_argument("--smoother", default="rbgs", choices=["rbgs", "jacobi"],
                     help="1-GPU arm: red-black GS (the BASELINE config) or damped Jacobi (omega = 2/3), both in the streaming kernel")
     ap.add_argument("--tolerance", type=float, default=None,
-                    help="absolute h-scaled L2 residual tolerance; default 1e-8 (reference) up to 4097^2, 1e-7 above: "
-                         "evaluating f - A u in fp64 has a rounding floor of ~eps*8/h^2*|u| = 3e-8 at h = 1/16384")
-    ap.add_argument("--cpu-n", type=int, default=8193, help="grid of the bounded CPU-baseline sample")
+                    help="absolute h-scaled L2 residual tolerance; default 1e-8 (the reference's).  Where that lies below "
+                         "the fp64 rounding floor of f - A u (~3e-8 at h = 1/16384) the solve ends on the floor rule of "
+                         "solvers/policy.py: one cycle after the residual stops contracting")
+    ap.add_argument("--cpu-n", type=int, default=None,
+                    help="grid of the CPU sample; default: 8193 for the cpu_baseline leg of the GPU arm (bounded to "
+                         "~10 s), the configured --n for --impl reference when the host has the memory for it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
@@ -80,15 +83,53 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock, power and throttle reasons sampled DURING the timed region.  The timed region of the default run
+    is tens of milliseconds, shorter than one period of `nvidia-smi -lms 200`, so the samples come from NVML directly
+    (nvidia_ml_py) on a 5 ms thread and carry timestamps; `mark()` brackets the timed window and the summary is
+    taken over the samples inside it.  Falls back to the nvidia-smi loop when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.gpu, self.proc, self.path = gpu_index, None, None
+    def __init__(self, gpu_index: int, period_s: float = 0.005):
+        self.gpu, self.period = gpu_index, period_s
+        self.proc, self.path, self.thread = None, None, None
+        self.samples = []          # (t, sm_mhz, power_w, reasons_bitmask)
+        self.window = [None, None]
+        self._stop = False
+        self.sm_max = None
+
+    def _nvml_loop(self, h, nv):
+        while not self._stop:
+            try:
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                     nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                                     if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons")
+                                     else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def __enter__(self):
+        try:
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(h, nv), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -99,7 +140,14 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark(self, which: int) -> None:
+        """mark(0) right before the timed region starts, mark(1) right after it ends."""
+        self.window[which] = time.perf_counter()
+
     def __exit__(self, *a):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
         if self.proc is not None:
             time.sleep(0.25)
             self.proc.terminate()
@@ -110,10 +158,32 @@ class ClockSampler:
 
     def summary(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            nv = self._nv
+            t0, t1 = self.window
+            inside = [s for s in self.samples if t0 is not None and t1 is not None and t0 <= s[0] <= t1]
+            use = inside if len(inside) >= 3 else self.samples
+            out["source"] = "nvml, %g ms period; %d of %d samples inside the timed window%s" % (
+                self.period * 1e3, len(inside), len(self.samples), "" if use is inside else " (too few: all samples used)")
+            if use:
+                sm = sorted(s[1] for s in use)
+                out.update({"samples": len(use), "sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": self.sm_max,
+                            "power_w_max": max(s[2] for s in use)})
+                bits = 0
+                for s in use:
+                    bits |= int(s[3])
+                names = {"hw_slowdown": "HwSlowdown", "hw_thermal_slowdown": "HwThermalSlowdown",
+                         "sw_thermal_slowdown": "SwThermalSlowdown", "sw_power_cap": "SwPowerCap"}
+                for key, suffix in names.items():
+                    mask = getattr(nv, "nvmlClocksEventReason" + suffix, None) or getattr(nv, "nvmlClocksThrottleReason" + suffix, 0)
+                    if bits & mask:
+                        out["reasons"].append(key)
+            return out
         try:
             rows = [l.strip().split(", ") for l in open(self.path) if l.strip()]
             sm = sorted(float(r[1]) for r in rows)
             out["samples"] = len(rows)
+            out["source"] = "nvidia-smi -lms 200"
             if sm:
                 out["sm_mhz"] = sm[len(sm) // 2]
                 out["sm_max_mhz"] = float(rows[0][2])
@@ -130,9 +200,9 @@ class ClockSampler:
 # CPU arm: the reference algorithm on the host cores (oracle port; the reference itself is pure-Python
 # loops at ~6e4 unknowns/s and does not exist on the GPU box)
 # ------------------------------------------------------------------------------------------------------
-def cpu_cycles(n: int, cycles: int, threads_hint=None):
-    """Time `cycles` V(2,2) RB-GS fp64 cycles of the C/OpenMP oracle on an n x n grid.
-    Returns (unknowns_per_s, seconds, threads_used, residual_history)."""
+def cpu_cycles(n: int, cycles: int, threads_hint=None, warmup: int = 0):
+    """Time `cycles` V(2,2) RB-GS fp64 cycles of the C/OpenMP oracle on an n x n grid, after `warmup` untimed cycles
+    (first-touch page faults, thread-pool start).  Returns (unknowns_per_s, seconds, threads_used, residual_history)."""
     import numpy as np
 
     from oracle import c_oracle as CO
@@ -142,6 +212,8 @@ def cpu_cycles(n: int, cycles: int, threads_hint=None):
     while (a - 1) % 2 == 0 and (a - 1) // 2 + 1 >= 5:
         a, L = (a - 1) // 2 + 1, L + 1
     f = O.mms_rhs(n)
+    if warmup > 0:
+        O.OracleMultigrid(n, max_levels=L, max_iterations=warmup, tolerance=0.0, ops=CO).solve(f)
     s = O.OracleMultigrid(n, max_levels=L, max_iterations=cycles, tolerance=0.0, ops=CO)
     t0 = time.perf_counter()
     _, info = s.solve(f)
@@ -165,16 +237,43 @@ def pick_cpu_threads():
     return best[0] if best else 1
 
 
-def run_cpu_baseline(n: int, cycles: int):
+def reference_python_timing():
+    """The reference's own Python classes timed in the build container (tools/time_reference_python.py; they cannot
+    travel to the GPU box): quoted beside the port so that both ends of "the reference's CPU path" are visible."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "reference_python_timing.json")))
+        return {"value": d["value"], "unit": d["unit"], "cores": 1, "where": d["where"],
+                "sample": "; ".join(f"{r['n']}x{r['n']}: {r['cycles']} cycles in {r['seconds']:.2f} s" for r in d["runs"])}
+    except Exception:
+        return None
+
+
+def run_cpu_baseline(n: int, cycles: int, warmup: int = 1):
     th = pick_cpu_threads()
     code = (f"import os,sys,json;os.environ['OMP_NUM_THREADS']='{th}';sys.path.insert(0,{ROOT!r});"
-            f"import bench;v,dt,t,h=bench.cpu_cycles({n},{cycles});print(json.dumps([v,dt,t,h]))")
+            f"import bench;v,dt,t,h=bench.cpu_cycles({n},{cycles},warmup={warmup});print(json.dumps([v,dt,t,h]))")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=1800)
     v, dt, t, hist = json.loads(out.stdout.strip().splitlines()[-1])
     return {"value": v, "unit": UNIT, "cores": int(t), "kind": "port",
-            "sample": f"{cycles} fp64 V(2,2) red-black GS cycles on {n}x{n} (C/OpenMP restatement of the reference "
-                      f"loops, oracle/mg_oracle.c; {dt:.1f} s; host has {os.cpu_count()} logical CPUs)",
-            "seconds": dt, "final_residual": hist[-1]}
+            "sample": f"{cycles} fp64 V(2,2) red-black GS cycles on {n}x{n} after {warmup} warm-up (C/OpenMP restatement "
+                      f"of the reference loops, oracle/mg_oracle.c; {dt:.1f} s; host has {os.cpu_count()} logical CPUs)",
+            "seconds": dt, "final_residual": hist[-1], "reference_python": reference_python_timing()}
+
+
+def reference_grid(a) -> int:
+    """Grid of the reference arm: the configured one when the host can hold it (the oracle keeps ~8 fp64 arrays per
+    level: ~23 GB at 16385^2), else the largest 2^k+1 below it that fits."""
+    if a.cpu_n:
+        return a.cpu_n
+    n = a.n
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 32 << 30
+    while n > 129 and 11.0 * n * n * 8 > 0.6 * avail:
+        n = (n - 1) // 2 + 1
+    return n
 
 
 def reference_arm(a):
@@ -182,13 +281,17 @@ def reference_arm(a):
     if rank != 0:
         return
     cyc = max(1, a.steps)
-    base = run_cpu_baseline(a.cpu_n, cyc)
+    n_ref = reference_grid(a)
+    wu = max(0, a.warmup)
+    base = run_cpu_baseline(n_ref, cyc, warmup=wu)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": a.gpus,
-            "steps": cyc, "warmup": 0, "ms_per_step": base["seconds"] / cyc * 1e3, "higher_is_better": True,
+            "steps": cyc, "warmup": wu, "ms_per_step": base["seconds"] / cyc * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"2D Poisson V(2,2) RB-GS cycles, fp64, CPU sample {a.cpu_n}x{a.cpu_n} of the "
-                                   f"{a.n}x{a.n} config (unknowns/s is size-independent: O(N) work per cycle)"},
-            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "config": {"workload": f"2D Poisson {n_ref}x{n_ref} manufactured sin*sin, V(2,2) red-black GS cycles, fp64 "
+                                   f"(the reference's CPU arithmetic: C/OpenMP port of its loops) "
+                                   + ("(BASELINE configs[2])" if n_ref == a.n else
+                                      f"-- bounded sample of the {a.n}x{a.n} config; unknowns/s is size-independent")},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "reference_python")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -213,7 +316,9 @@ def gpu_arm(a):
         dist.init_process_group("nccl", device_id=dev)
     n = a.n
     peak, peak_src = load_peaks()
-    tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
+    # the reference's tolerance; where it lies below the fp64 rounding floor of the residual evaluation (16385^2) the
+    # solve ends on the floor rule of solvers/policy.py and says so in config.stopped_on
+    tol = a.tolerance if a.tolerance is not None else 1e-8
 
     if world > 1:
         from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import run_distributed_bench
@@ -227,6 +332,7 @@ def gpu_arm(a):
         dist.destroy_process_group()
         return
 
+    from mixed_precision_multigrid_solvers_for_pdes_b200.solvers.policy import CONTINUE
     solver = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
                                      cycle_type=a.cycle, loader=a.loader, max_iterations=10 ** 9, device=dev,
                                      smoother=a.smoother,
@@ -235,38 +341,37 @@ def gpu_arm(a):
     eng, g = solver._engine, solver._grid
     b64 = eng.levels[0].bufs(torch.float64)
     ops.fill_sinsin_(b64.f, (0.0, 1.0, 0.0, 1.0), 2 * np.pi ** 2, 1.0, 1.0)
+    ops.zero_ring_(b64.f)
 
-    # the solve loop of MixedPrecisionMultigrid.solve, unrolled into steps
-    state = {"phase": None, "hist": [], "solves": 0, "cycles_per_solve": [], "precisions": []}
+    # the solve loop of MixedPrecisionMultigrid.solve, unrolled into steps: same policy object, same launches
+    state = {"pol": None, "first": True, "solves": 0, "cycles_per_solve": [], "precisions": [], "stopped_on": None}
 
     def restart():
-        b64.u.zero_()
-        state["phase"] = "refine" if solver.mode in ("switch", "refine") else solver.mode
-        state["hist"] = []
-        if state["phase"] == "refine":
-            solver._refinement_residual()
-        elif state["phase"] == "fp32":
-            b32 = eng.levels[0].bufs(torch.float32)
-            ops.cast(b64.f, torch.float32, out=b32.f)
-            b32.u.zero_()
+        pol = state["pol"] = solver.make_policy()
+        state["first"] = True  # the zero initial guess is neither memset nor read (U_ZERO passes)
+        if pol.phase == "refine":
+            solver._refinement_residual(u_zero=True)
+        elif pol.phase == "fp32":
+            ops.cast(b64.f, torch.float32, out=eng.levels[0].bufs(torch.float32).f)
 
     def step():
-        ph = state["phase"]
+        pol = state["pol"]
+        ph, first = pol.phase, state["first"]
+        state["first"] = False
         if ph == "refine":
-            norm = solver._cycle_refinement()
+            norm = solver._cycle_refinement(u_zero=first)
         elif ph == "fp64":
-            norm = solver._cycle_fp64()
+            norm = solver._cycle_fp64(u_zero=first)
         else:
-            norm = solver._cycle_fp32_only()
-        state["hist"].append(norm)
+            norm = solver._cycle_fp32_only(u_zero=first)
         state["precisions"].append(ph)
-        if norm < solver.tolerance or len(state["hist"]) >= 30:
+        if pol.observe(norm) != CONTINUE or len(pol.history) >= 30:
             state["solves"] += 1
-            state["cycles_per_solve"].append(len(state["hist"]))
-            state["last_hist"] = list(state["hist"])
+            state["cycles_per_solve"].append(len(pol.history))
+            state["last_hist"] = list(pol.history)
+            state["stopped_on"] = pol.stopped_on
+            state["floor_bound"] = pol.floor_bound
             restart()
-        elif ph == "refine" and solver.mode == "switch" and norm <= solver.switch_threshold:
-            state["phase"] = "fp64"
 
     restart()
     # setup (untimed, like a compile step): whole solves until every (phase, buffer-role) CUDA graph the solve
@@ -280,14 +385,16 @@ def gpu_arm(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         torch.cuda.synchronize()
+        clk.mark(0)
         e0.record()
         for _ in range(a.steps):
             step()
         e1.record()
         torch.cuda.synchronize()
+        clk.mark(1)
         ms = e0.elapsed_time(e1)
         # keep the GPU under the same load until the sampler (200 ms period) has seen it for >= 1.5 s; untimed
-        t_end = time.perf_counter() + max(0.0, 1.5 - ms * 1e-3)
+        t_end = time.perf_counter() + (max(0.0, 1.5 - ms * 1e-3) if clk.thread is None else 0.0)  # nvidia-smi fallback only
         while time.perf_counter() < t_end:
             step()
         torch.cuda.synchronize()
@@ -298,7 +405,7 @@ def gpu_arm(a):
     # per-kernel durations: the same K steps once more, eagerly (CUDA events cannot be recorded inside a
     # replayed graph), with an event pair around every level-0 launch on the launching stream
     solver.use_cuda_graphs = False
-    ops.TIMER = ops.KernelTimer(min_points=n * n // 2)
+    ops.TIMER = ops.KernelTimer(min_points=0)  # every level: the cycle's own algorithmic bytes come from this list
     launches0 = _lib.call("mg_launch_count")
     t0e = torch.cuda.Event(enable_timing=True)
     t1e = torch.cuda.Event(enable_timing=True)
@@ -313,17 +420,24 @@ def gpu_arm(a):
     ops.TIMER = None
     solver.use_cuda_graphs = not a.no_graphs
 
-    # roofline of the dominant kernel (largest total time among the level-0 fused passes)
+    # roofline of the dominant kernel (largest total time among the fused passes)
     def alg_bytes(tag):
-        name, dt, _ = tag.split("/")
+        """Algorithmic HBM bytes of one launch, from the pass's own grid."""
+        name, dt, dims = tag.split("/")
+        px, py = (int(v) for v in dims.split("x"))
+        pts = px * py
         w = 8 if dt == "f64" else 4
-        if "resid32" in name or name.startswith("update"):
+        if name.startswith("small"):      # whole coarse sub-cycle in shared memory: read f (+u), write u
+            return 2.0 * w * pts
+        if "resid32" in name or "update" in name:
             b = 0.0
             if "resid32" in name:
                 b += 8 + 8 + 4            # read u64, f64; write r32
-            if name.startswith("update"):
+            if "update" in name:
                 b += 4 + 8                # read e32; write u64
-            return b * n * n
+            if name.startswith("Z+"):
+                b -= 8                    # the zero iterate is not read
+            return b * pts
         b = 3.0 * w                       # read u, read f, write u
         if name.startswith("Z+"):
             b -= w                        # the zero iterate is not read
@@ -331,10 +445,14 @@ def gpu_arm(a):
             b += 0.25 * w                 # read the coarse correction
         if "+R" in name:
             b += 0.25 * w                 # write the restricted residual
-        return b * n * n
+        return b * pts
     roof = None
     kernels = {}
+    cycle_bytes = 0.0
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
+        cycle_bytes += alg_bytes(tag) * d["launches"]
+        if not tag.endswith(f"/{n}x{n}"):
+            continue                      # the per-kernel table lists level 0; coarser levels enter cycle_roofline
         ach = alg_bytes(tag) / (d["mean_ms"] * 1e-3) / 1e9
         sm = "rbgs" if "rbgs" in tag else ("jac" if "jac" in tag else None)
         sweeps = int(tag.split(sm)[1][0]) if sm else 0
@@ -346,13 +464,17 @@ def gpu_arm(a):
             roof = {"bound": "hbm", "kernel": tag, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                     "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg_bytes(tag)}
+    coarse_ms = sum(d["total_ms"] for t, d in kern.items() if not t.endswith(f"/{n}x{n}")) / a.steps
     tr = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if roof is not None and os.path.exists(tr):
         try:
             roof["traffic"] = json.load(open(tr)).get(roof["kernel"])
         except Exception:
             pass
-    cycle_frac = BYTES_PER_UNKNOWN_FP64_V22 * value / 1e9 / peak
+    # whole-cycle roofline from the bytes of the passes that actually ran (all levels, restarts included)
+    bpu = cycle_bytes / a.steps / (n * n)
+    cycle_frac = bpu * value / 1e9 / peak
+    assert cycle_frac <= 1.05, f"cycle roofline fraction {cycle_frac:.3f} > 1: the byte model is wrong"
 
     # end to end through the public API with HOST buffers (pinned): H2D of f, solve, D2H of u
     e2e = None
@@ -398,7 +520,7 @@ def gpu_arm(a):
         del outs
         del f_host
 
-    cpu = None if a.no_cpu_baseline else run_cpu_baseline(a.cpu_n, 8)
+    cpu = None if a.no_cpu_baseline else run_cpu_baseline(a.cpu_n or 8193, 8)
     clocks = clk.summary()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": max(3, a.warmup),
@@ -412,11 +534,15 @@ def gpu_arm(a):
                    "loader": a.loader, "cuda_graphs": (not a.no_graphs), "graphs_captured": replayed, "priming_solves": primed,
                    "kernel_timing": "eager replay of the same %d steps with CUDA events around each level-0 launch "
                                     "(%.3f ms/step eager)" % (a.steps, ms_eager / a.steps), "tolerance": tol, "switch_threshold": 1e-6, "l2": "inputs (>= 1 GB per array) exceed the 126 MB L2; no flush needed",
-                   "cycles_per_solve": state["cycles_per_solve"][-3:], "last_residual_history": state.get("last_hist")},
+                   "cycles_per_solve": state["cycles_per_solve"][-3:], "last_residual_history": state.get("last_hist"),
+                   "stopped_on": state.get("stopped_on"), "attainable_residual_bound": state.get("floor_bound")},
         "roofline": roof, "kernels": kernels,
-        "cycle_roofline": {"bytes_per_unknown": BYTES_PER_UNKNOWN_FP64_V22, "note": "fp64 fused-minimum model, SURVEY 8d",
-                           "frac_of_peak": round(cycle_frac, 4)},
-        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "cycle_roofline": {"bytes_per_unknown": round(bpu, 2), "frac_of_peak": round(cycle_frac, 4),
+                           "note": "algorithmic bytes of every pass launched per step (all levels, restart passes "
+                                   "included) / unknowns; whole-step time from the graph-replayed timed region",
+                           "coarse_levels_ms_per_step_eager": round(coarse_ms, 4),
+                           "survey_fp64_model_bytes_per_unknown": BYTES_PER_UNKNOWN_FP64_V22},
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "reference_python")} if cpu else None),
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

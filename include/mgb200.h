@@ -149,6 +149,12 @@ MG_API int mg_axpy(double alpha, const void* x, void* y, int nx, int ny, int64_t
 /* x = 0 over the full pitched (nx, ld) extent. */
 MG_API int mg_zero(void* x, int nx, int64_t ld, int dtype, void* stream);
 
+/* Zero the boundary ring of a field: first and last column always, first / last row when the flag is set (a row slab
+ * holds them only on the physical boundary).  The reference's residual equals f on the ring and its norm sums over ALL
+ * points (operators/laplacian.py:64,117; core/grid.py:187): a source that does not vanish there can never meet the
+ * tolerance although those values enter no equation, so the facade clears the ring of f. */
+MG_API int mg_zero_ring(void* x, int nx, int ny, int64_t ld, int first_row, int last_row, int dtype, void* stream);
+
 /* f[i][j] = amplitude * sin(kx*pi*x_i) * sin(ky*pi*y_j), x_i = x0 + i*(x1-x0)/(nx-1) evaluated in
  * fp64 and rounded to dtype (synthetic manufactured-solution data generated in HBM; the
  * README problem README.md:77-78 is amplitude = 2*pi^2, kx = ky = 1). */
@@ -228,7 +234,9 @@ MG_API int mg_vc_pass(const void* u_in, void* u_out, const void* f, const void* 
  *     u_out = u_in + (double) e_in            (e_in: fp32 fine-grid correction; NULL: u unchanged, no store)
  *     r_out = (float) (f - coefficient*lap_h u_out)   (r_out: fp32; NULL: no residual stage)
  *     sumsq_out[0] = sum over all points of the fp64 residual squared (needs workspace)
- * u, f are fp64; out of place (u_out != u_in). */
+ * u, f are fp64; out of place (u_out != u_in).  flags: MG_VC_LOADER_CPASYNC, MG_VC_ROWS, and MG_VC_U_ZERO (u_in is
+ * identically zero and is not read: the first passes of a solve from the zero initial guess, multigrid.py:208-211,
+ * then need neither a memset of the iterate nor its 8 bytes per point of read traffic). */
 MG_API int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
                       double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
                       int64_t ld_f, int64_t ld_e, int64_t ld_r, double hx, double hy, double coefficient,
@@ -282,7 +290,10 @@ MG_API int mg_vc_prolong_correct_smooth(const void* u_in, void* u_out, const voi
  * Usable when mg_small_cycle_smem_bytes(...) <= 200 KiB (e.g. 129^2 fp32 or 65^2 fp64 entry levels);
  * returns MG_ERR_UNSUPPORTED otherwise.  A W-cycle at 32769^2 visits the coarsest grid 8192 times: this
  * kernel replaces ~12 launches per visit by one.  `info` (device, 2 doubles, may be NULL) = {sweeps, norm} of
- * the last coarse solve; u_zero != 0: start from u = 0 without reading u. */
+ * the last coarse solve; u_zero bit 0: start from u = 0 without reading u; bit 1 (profiling aid): `info` holds 16
+ * doubles and the kernel ADDS SM clock cycles to info[2..5] = {smoothing, residual + restriction, prolongation, coarsest
+ * solve} of the whole-block levels, info[6..9] = the same for the levels worked on by warp 0 alone (grids up to
+ * 17 x 17), info[10..12] = {load, cycle, store}, info[13] = launches. */
 MG_API int mg_small_cycle_smem_bytes(int nx, int ny, int nlev, int dtype, int coarse_dtype);
 MG_API int mg_small_cycle(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double hx, double hy,
                    int nlev, int cycle, int pre, int post, double omega, double coefficient, double shift,

@@ -325,6 +325,20 @@ __global__ void store_doubles_kernel(const double* __restrict__ src, double* __r
   for (int k = threadIdx.x; k < n; k += blockDim.x) dst[k] = src[k];
 }
 
+// zero the first / last column and optionally the first / last row: thread t handles row t and column t
+template <typename T>
+__global__ void zero_ring_kernel(T* __restrict__ x, int nx, int ny, int64_t ld, int first_row, int last_row) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < nx) {
+    x[(int64_t)t * ld] = (T)0;
+    x[(int64_t)t * ld + ny - 1] = (T)0;
+  }
+  if (t < ny) {
+    if (first_row) x[t] = (T)0;
+    if (last_row) x[(int64_t)(nx - 1) * ld + t] = (T)0;
+  }
+}
+
 void reduce_partials_sum(const double* partials, int n, double* out, cudaStream_t st) {
   final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(partials, n, out);
 }
@@ -624,6 +638,18 @@ int mg_zero(void* x, int nx, int64_t ld, int dtype, void* stream) {
   const size_t esz = dtype == MG_F64 ? 8 : 4;
   cudaMemsetAsync(x, 0, (size_t)nx * ld * esz, as_stream(stream));
   return check_launch("mg_zero", 0);
+}
+
+int mg_zero_ring(void* x, int nx, int ny, int64_t ld, int first_row, int last_row, int dtype, void* stream) {
+  MG_REQUIRE(x && nx >= 1 && ny >= 1 && ld >= ny);
+  if (!valid_dtype(dtype)) return MG_ERR_DTYPE;
+  const int n = nx > ny ? nx : ny;
+  cudaStream_t st = as_stream(stream);
+  if (dtype == MG_F64)
+    zero_ring_kernel<double><<<(n + 255) / 256, 256, 0, st>>>((double*)x, nx, ny, ld, first_row, last_row);
+  else
+    zero_ring_kernel<float><<<(n + 255) / 256, 256, 0, st>>>((float*)x, nx, ny, ld, first_row, last_row);
+  return check_launch("mg_zero_ring");
 }
 
 int mg_fill_sinsin(void* f, int nx, int ny, int64_t ld, double x0, double x1, double y0, double y1,

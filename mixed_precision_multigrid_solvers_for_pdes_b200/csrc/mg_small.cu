@@ -20,7 +20,7 @@ namespace mg {
 namespace small {
 
 constexpr int MAXLEV = 8;
-constexpr int THREADS = 1024;
+constexpr int THREADS = 512;  // 128 registers per thread: the register-resident coarsest solve must not spill
 
 template <typename T, typename TC> struct Params {
   int nlev;
@@ -34,7 +34,11 @@ template <typename T, typename TC> struct Params {
   int cycle;  // 0 V, 1 W, 2 F
   int pre, post;
   int u_zero;
+  int profile;  // 1: info[2..9] += SM cycles spent per phase kind (see mg_small_cycle in mgb200.h); info holds 16 doubles
   int iso1;  // hx == hy and omega == 1: the streaming kernel's 5-instruction point update (same bits as there)
+  int warp_start;  // first level worked on by warp 0 alone (all sides <= WARP_TEAM_MAX); nlev if none
+  int exact5;      // coarsest grid is 5 x 5 with dyadic isotropic spacing, no shift, coefficient -1: register solver
+  double xthr;     // largest double whose square root is below ctol (exact5 stopping test without a sqrt per sweep)
   T* u;
   const T* f;
   int64_t ld_u, ld_f;
@@ -56,9 +60,40 @@ __device__ __forceinline__ T resid_at(const T* u, const T* f, int nx, int ny, in
               : residual_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], fv);
 }
 
-template <typename T>
-__device__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, int sweeps, bool iso1) {
+// ---------------------------------------------------------------------------------------------------------
+// Teams.  A level is worked on either by the whole block (rows over warps, columns over lanes, __syncthreads
+// between phases) or -- grids of at most 17 x 17 -- by WARP 0 ALONE with __syncwarp between phases: a phase on
+// such a grid is one or two instructions per lane, and a 32-warp barrier costs more than the phase itself.
+// A W-cycle visits these levels thousands of times per fine-grid cycle.
+// ---------------------------------------------------------------------------------------------------------
+template <bool WARP> __device__ __forceinline__ void team_sync() {
+  if (WARP) __syncwarp();
+  else __syncthreads();
+}
+constexpr int WARP_TEAM_MAX = 17;  // largest side of a level handled by the warp team
+
+template <typename T, bool WARP>
+__device__ __forceinline__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, int sweeps, bool iso1) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (WARP) {
+    // lane = r * W + c: W = power of two >= points of one colour per row, 32 / W rows per step
+    const int half = (ny - 1) >> 1;                       // ceil((ny - 2) / 2)
+    const int wl = half <= 2 ? 1 : (half <= 4 ? 2 : (half <= 8 ? 3 : (half <= 16 ? 4 : 5)));
+    const int r = lane >> wl, c = lane & ((1 << wl) - 1), rstep = 32 >> wl;
+    for (int k = 0; k < sweeps; ++k)
+      for (int col = 0; col < 2; ++col) {
+        for (int i = 1 + r; i <= nx - 2; i += rstep) {
+          const int j = 1 + ((i + 1 + col) & 1) + 2 * c;
+          if (j <= ny - 2) {
+            T* p = u + i * ny + j;
+            p[0] = iso1 ? relax_iso1<T>(s, p[ny], p[-ny], p[1], p[-1], f[i * ny + j])
+                        : relax_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], f[i * ny + j]);
+          }
+        }
+        __syncwarp();
+      }
+    return;
+  }
   for (int k = 0; k < sweeps; ++k)
     for (int c = 0; c < 2; ++c) {
       for (int i = 1 + warp; i <= nx - 2; i += THREADS / 32)      // rows over warps, columns over lanes
@@ -72,11 +107,11 @@ __device__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>
 }
 
 // f_c = R(f - A u): injection on the coarse boundary, full weighting inside, reference summation order
-template <typename T, typename TO>
-__device__ void restrict_residual(const T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, TO* fc, int nxc,
+template <typename T, typename TO, bool WARP>
+__device__ __forceinline__ void restrict_residual(const T* u, const T* f, int nx, int ny, const StencilScalars<T>& s, TO* fc, int nxc,
                                   int nyc, bool iso1) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int I = warp; I < nxc; I += THREADS / 32)
+  const int warp = WARP ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  for (int I = warp; I < nxc; I += (WARP ? 1 : THREADS / 32))
    for (int J = lane; J < nyc; J += 32) {
     const int idx = I * nyc + J, i = 2 * I, j = 2 * J;
     T v;
@@ -93,14 +128,14 @@ __device__ void restrict_residual(const T* u, const T* f, int nx, int ny, const 
     }
     fc[idx] = (TO)v;
   }
-  __syncthreads();
+  // no barrier here: the caller zeroes the coarse iterate next and synchronises once for both
 }
 
 // u += P e_c, bilinear with the reference's last-row / last-column treatment (transfer.py:234-267)
-template <typename T, typename TI>
-__device__ void prolong_add(T* u, int nx, int ny, const TI* ec, int nyc) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < nx; i += THREADS / 32)
+template <typename T, typename TI, bool WARP>
+__device__ __forceinline__ void prolong_add(T* u, int nx, int ny, const TI* ec, int nyc) {
+  const int warp = WARP ? 0 : (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  for (int i = warp; i < nx; i += (WARP ? 1 : THREADS / 32))
    for (int j = lane; j < ny; j += 32) {
     const int idx = i * ny + j;
     const TI* c = ec + (i >> 1) * nyc + (j >> 1);
@@ -112,53 +147,243 @@ __device__ void prolong_add(T* u, int nx, int ny, const TI* ec, int nyc) {
     else v = (T)0.25 * ((((T)c[0] + (T)c[1]) + (T)c[nyc]) + (T)c[nyc + 1]);
     u[idx] += v;
   }
-  __syncthreads();
+  team_sync<WARP>();
 }
 
-// coarsest level: <= cmaxit x [lexicographic GS sweep along anti-diagonals, residual, h-scaled norm], strict arithmetic
+// ---------------------------------------------------------------------------------------------------------
+// Coarsest level: <= cmaxit x [lexicographic GS sweep, residual, h-scaled norm] (solvers/base.py:258-285).
+// Every variant evaluates the SAME rounded operations in the same order as mg_coarse_solve_lexgs.
+// ---------------------------------------------------------------------------------------------------------
+
+// (a) The 5 x 5 coarsest grid of every 2^k + 1 hierarchy, isotropic dyadic spacing, omega = 1, no shift, coefficient -1:
+// ONE THREAD, all 25 values in registers.  A W-cycle over 14 levels makes 8192 coarsest solves of ~12 sweeps each, all
+// on the critical path, so what matters is the latency of one sweep + stopping test:
+//   * power-of-two scalings commute with rounding, so the point update ((up+dn)/h^2 + (rt+lf)/h^2 + f) / (4/h^2) equals
+//     (((up+dn)+(rt+lf)) + h^2 f) * 0.25 and the residual f - (-(S/h^2 - u*4/h^2)) equals (h^2 f + fma(-4, u, S)) / h^2
+//     bit for bit (checked on the CPU against the strict expressions on 12M random inputs); 4 and 3 dependent
+//     operations instead of 9 and 9;
+//   * the squared residuals are summed in the order of the strict kernel's lane-strided warp tree (leaf k = point k,
+//     partners k ^ 16, 8, 4, 2, 1); the common factor 1/h^4 is applied once to the sum (exact);
+//   * sqrt is monotone and correctly rounded, so "sqrt(x) < tol" is decided as "x <= xthr" with xthr the largest double
+//     whose root is below tol (found on the host);
+//   * the test of sweep k is evaluated while sweep k+1 is already running (software pipelining: both are straight-line
+//     code in one basic block; there is no speculation in hardware), and the extra sweep is dropped when k passed.
+template <typename TC> struct Scal5 { TC hx2, ihx2, inv_neg_diag; };  // by value: no local copy of the kernel parameters
+
+// ZB: the boundary values of u and of f are all zero (every coarse error equation of a solve whose right-hand side
+// vanishes on the boundary ring -- the facade's default): the boundary terms drop out of the sums (x + 0 = x) and out
+// of the norm tree, which leaves 27 + 44 fp64 instructions per sweep + test and few enough live values for registers.
+template <typename TC, bool ZB>
+__device__ __forceinline__ void coarse_solve_5x5_exact(TC* u, const TC* f, const Scal5<TC>& s, double hxhy,
+                                                       double xthr, int maxit, double* info) {
+  using A = Strict<TC>;
+  TC U[5][5], G[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const bool in = i >= 1 && i <= 3 && j >= 1 && j <= 3;
+      U[i][j] = (ZB && !in) ? (TC)0 : u[i * 5 + j];
+      G[i][j] = (ZB && !in) ? (TC)0 : A::mul(f[i * 5 + j], s.hx2);  // h^2 f (exact scaling)
+    }
+  const TC quarter = A::mul(s.ihx2, s.inv_neg_diag);       // 1/h^2 * h^2/4 = 1/4 exactly
+  const double ih4 = (double)s.ihx2 * (double)s.ihx2;      // power of two
+
+  // x + y where an operand known to be the zero boundary value is dropped at compile time (after unrolling)
+  auto add2 = [&](bool ha, TC a, bool hb, TC b) -> TC {
+    if (ha && hb) return A::add(a, b);
+    return ha ? a : (hb ? b : (TC)0);
+  };
+  auto nbsum = [&](const TC(&V)[5][5], int i, int j) -> TC {
+    const bool hu = !ZB || i + 1 <= 3, hd = !ZB || i - 1 >= 1, hr = !ZB || j + 1 <= 3, hl = !ZB || j - 1 >= 1;
+    const TC t1 = add2(hu, V[i + 1][j], hd, V[i - 1][j]);
+    const TC t2 = add2(hr, V[i][j + 1], hl, V[i][j - 1]);
+    return add2(hu || hd, t1, hr || hl, t2);
+  };
+  auto sweep = [&](TC(&V)[5][5]) {
+#pragma unroll
+    for (int i = 1; i <= 3; ++i)
+#pragma unroll
+      for (int j = 1; j <= 3; ++j) V[i][j] = A::mul(A::add(G[i][j], nbsum(V, i, j)), quarter);
+  };
+  auto normx = [&](const TC(&V)[5][5]) -> double {
+    // leaves of the strict kernel's warp tree: leaf k = point k = 5 i + j, partners k ^ 16, 8, 4, 2, 1
+    double a[32];
+    bool nz[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) { a[k] = 0.0; nz[k] = false; }
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const bool in = i >= 1 && i <= 3 && j >= 1 && j <= 3;
+        if (in) {
+          const TC w = A::add(G[i][j], fma((TC)-4, V[i][j], nbsum(V, i, j)));   // h^2 (f - A u)
+          a[i * 5 + j] = (double)A::mul(w, w);
+          nz[i * 5 + j] = true;
+        } else if (!ZB) {
+          a[i * 5 + j] = (double)A::mul(G[i][j], G[i][j]);  // r = f on the boundary (loop invariant: hoisted)
+          nz[i * 5 + j] = true;
+        }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int k = 0; k < o; ++k) {
+        if (nz[k] && nz[k + o]) a[k] = __dadd_rn(a[k], a[k + o]);
+        else if (nz[k + o]) a[k] = a[k + o];                 // 0 + x = x for the non-negative squares
+        nz[k] = nz[k] || nz[k + o];
+      }
+    return __dmul_rn(hxhy, __dmul_rn(a[0], ih4));
+  };
+
+  TC W[5][5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+#pragma unroll
+    for (int j = 0; j < 5; ++j) W[i][j] = U[i][j];
+  sweep(U);  // U = state after sweep 1
+  int it = 1;
+  double x;
+  while (true) {
+#pragma unroll
+    for (int i = 1; i <= 3; ++i)
+#pragma unroll
+      for (int j = 1; j <= 3; ++j) W[i][j] = U[i][j];
+    sweep(W);         // state after sweep it + 1, started before the test of sweep `it` is known
+    x = normx(U);
+    if (x <= xthr || it >= maxit) break;
+#pragma unroll
+    for (int i = 1; i <= 3; ++i)
+#pragma unroll
+      for (int j = 1; j <= 3; ++j) U[i][j] = W[i][j];
+    ++it;
+  }
+#pragma unroll
+  for (int i = 1; i <= 3; ++i)
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) u[i * 5 + j] = U[i][j];
+  if (info != nullptr) {
+    info[0] = (double)it;
+    info[1] = sqrt(x);
+  }
+}
+
 template <typename TC>
-__device__ void coarse_solve(TC* u, const TC* f, int nx, int ny, const StencilScalars<TC>& s, double hxhy, double tol,
-                             int maxit, double* red, double* info) {
+__device__ __noinline__ void coarse_solve_5x5(TC* u, const TC* f, const Scal5<TC> s, double hxhy, double xthr, int maxit,
+                                              double* info) {
+  bool zb = true;
+#pragma unroll
+  for (int k = 0; k < 25; ++k) {
+    const int i = k / 5, j = k % 5;
+    if (!(i >= 1 && i <= 3 && j >= 1 && j <= 3)) zb = zb && u[k] == (TC)0 && f[k] == (TC)0;
+  }
+  if (zb) coarse_solve_5x5_exact<TC, true>(u, f, s, hxhy, xthr, maxit, info);
+  else coarse_solve_5x5_exact<TC, false>(u, f, s, hxhy, xthr, maxit, info);
+}
+
+// (b) Any coarsest grid of at most 32 points: one point per LANE, values in registers, neighbours by warp shuffle (no
+// shared-memory round trip per anti-diagonal).  Strict arithmetic, same sweep order, residual, summation tree and stopping
+// rule as (c).
+template <typename TC>
+__device__ __forceinline__ void coarse_solve_lanes(TC* u, const TC* f, int nx, int ny, const StencilScalars<TC>& s, double hxhy, double tol,
+                                   int maxit, double* info) {
+  const int lane = threadIdx.x & 31, n = nx * ny;
+  const int k = lane < n ? lane : 0;
+  const int i = k / ny, j = k - i * ny;
+  const bool inside = lane < n && i > 0 && i < nx - 1 && j > 0 && j < ny - 1;
+  TC uk = lane < n ? u[k] : (TC)0;
+  const TC fk = lane < n ? f[k] : (TC)0;
+  // shuffle sources, clamped into the warp (values fetched by non-interior lanes are never used)
+  const int kup = min(k + ny, 31), kdn = max(k - ny, 0), krt = min(k + 1, 31), klf = max(k - 1, 0);
   int it = 1;
   double norm = 0.0;
+  for (; it <= maxit; ++it) {
+    for (int d = 2; d <= nx + ny - 4; ++d) {
+      const TC up = __shfl_sync(0xffffffffu, uk, kup), dn = __shfl_sync(0xffffffffu, uk, kdn);
+      const TC rt = __shfl_sync(0xffffffffu, uk, krt), lf = __shfl_sync(0xffffffffu, uk, klf);
+      if (inside && i + j == d) uk = relax_strict<TC>(s, uk, up, dn, rt, lf, fk);
+    }
+    const TC up = __shfl_sync(0xffffffffu, uk, kup), dn = __shfl_sync(0xffffffffu, uk, kdn);
+    const TC rt = __shfl_sync(0xffffffffu, uk, krt), lf = __shfl_sync(0xffffffffu, uk, klf);
+    TC v = fk;  // r = f on the boundary; lanes beyond the grid hold f = 0
+    if (inside) v = Strict<TC>::sub(v, apply_strict<TC>(s, uk, up, dn, rt, lf));
+    double acc = 0.0;
+    acc += (double)Strict<TC>::mul(v, v);
+    acc = warp_sum(acc);
+    norm = sqrt(hxhy * acc);
+    if (norm < tol) break;
+  }
+  if (inside) u[k] = uk;
+  if (info != nullptr && lane == 0) {
+    info[0] = (double)(it > maxit ? maxit : it);
+    info[1] = norm;
+  }
+}
+
+// warp 0 only; no block barrier (the caller synchronises the team)
+template <typename TC>
+__device__ __forceinline__ void coarse_solve_warp(TC* u, const TC* f, int nx, int ny, const StencilScalars<TC>& s, double hxhy, double tol,
+                                  double xthr, int exact5, int maxit, double* info) {
+  const int lane = threadIdx.x & 31;
+  if (exact5) {  // uniform
+    if (lane == 0) coarse_solve_5x5<TC>(u, f, Scal5<TC>{s.hx2, s.ihx2, s.inv_neg_diag}, hxhy, xthr, maxit, info);
+    __syncwarp();
+    return;
+  }
+  if (nx * ny <= 32) {
+    coarse_solve_lanes<TC>(u, f, nx, ny, s, hxhy, tol, maxit, info);
+    __syncwarp();
+    return;
+  }
+  // (c) up to 32 x 32 interior points: anti-diagonal wavefronts through shared memory
+  int it = 1;
+  double norm = 0.0;
+  for (; it <= maxit; ++it) {
+    for (int d = 2; d <= nx + ny - 4; ++d) {
+      const int ilo = max(1, d - (ny - 2)), ihi = min(nx - 2, d - 1);
+      const int i = ilo + lane;
+      if (i <= ihi) {
+        const int j = d - i;
+        TC* p = u + i * ny + j;
+        p[0] = relax_strict<TC>(s, p[0], p[ny], p[-ny], p[1], p[-1], f[i * ny + j]);
+      }
+      __syncwarp();
+    }
+    double acc = 0.0;
+    for (int k = lane; k < nx * ny; k += 32) {
+      const int i = k / ny, j = k - i * ny;
+      TC v = f[k];
+      if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+        const TC* p = u + k;
+        v = Strict<TC>::sub(v, apply_strict<TC>(s, p[0], p[ny], p[-ny], p[1], p[-1]));
+      }
+      acc += (double)Strict<TC>::mul(v, v);
+    }
+    acc = warp_sum(acc);
+    norm = sqrt(hxhy * acc);
+    __syncwarp();
+    if (norm < tol) break;
+  }
+  if (info != nullptr && lane == 0) {
+    info[0] = (double)(it > maxit ? maxit : it);
+    info[1] = norm;
+  }
+  __syncwarp();
+}
+
+// whole block; ends with a block barrier
+template <typename TC>
+__device__ __forceinline__ void coarse_solve(TC* u, const TC* f, int nx, int ny, const StencilScalars<TC>& s, double hxhy, double tol,
+                             double xthr, int exact5, int maxit, double* red, double* info) {
   if (nx - 2 <= 32 && ny - 2 <= 32 && nx * ny <= 1024) {
     // tiny grid: one warp does everything with warp-level synchronisation; the rest of the block just waits
-    if (threadIdx.x < 32) {
-      const int lane = threadIdx.x;
-      for (; it <= maxit; ++it) {
-        for (int d = 2; d <= nx + ny - 4; ++d) {
-          const int ilo = max(1, d - (ny - 2)), ihi = min(nx - 2, d - 1);
-          const int i = ilo + lane;
-          if (i <= ihi) {
-            const int j = d - i;
-            TC* p = u + i * ny + j;
-            p[0] = relax_strict<TC>(s, p[0], p[ny], p[-ny], p[1], p[-1], f[i * ny + j]);
-          }
-          __syncwarp();
-        }
-        double acc = 0.0;
-        for (int k = lane; k < nx * ny; k += 32) {
-          const int i = k / ny, j = k - i * ny;
-          TC v = f[k];
-          if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
-            const TC* p = u + k;
-            v = Strict<TC>::sub(v, apply_strict<TC>(s, p[0], p[ny], p[-ny], p[1], p[-1]));
-          }
-          acc += (double)Strict<TC>::mul(v, v);
-        }
-        acc = warp_sum(acc);
-        norm = sqrt(hxhy * acc);
-        __syncwarp();
-        if (norm < tol) break;
-      }
-      if (info != nullptr && lane == 0) {
-        info[0] = (double)(it > maxit ? maxit : it);
-        info[1] = norm;
-      }
-    }
+    if (threadIdx.x < 32) coarse_solve_warp<TC>(u, f, nx, ny, s, hxhy, tol, xthr, exact5, maxit, info);
     __syncthreads();
     return;
   }
+  int it = 1;
+  double norm = 0.0;
   for (; it <= maxit; ++it) {
     for (int d = 2; d <= nx + ny - 4; ++d) {
       const int ilo = max(1, d - (ny - 2)), ihi = min(nx - 2, d - 1);
@@ -190,6 +415,83 @@ __device__ void coarse_solve(TC* u, const TC* f, int nx, int ny, const StencilSc
   __syncthreads();
 }
 
+// The V / W / F recursion of solvers/multigrid.py:253-337 over levels lstart .. L-1, iteratively, by one team.
+// The block team hands the sub-cycle of the levels from p.warp_start on to warp 0 (run_cycle<.., true>) and waits.
+template <typename T, typename TC, bool WARP>
+__device__ __forceinline__ void run_cycle(const Params<T, TC>& p, unsigned char* sm, double* red, int lstart) {
+  const int L = p.nlev, last = L - 1;
+  auto U = [&](int l) { return reinterpret_cast<T*>(sm + p.off_u[l]); };
+  auto F = [&](int l) { return reinterpret_cast<T*>(sm + p.off_f[l]); };
+  TC* const uc = reinterpret_cast<TC*>(sm + p.off_u[last]);
+  TC* const fc = reinterpret_cast<TC*>(sm + p.off_f[last]);
+  const bool iso1 = p.iso1 != 0;
+  int rep[MAXLEV];
+  int l = lstart;
+  bool down = true;
+  // optional phase profile (one thread's clock; phases end with a team barrier, so this is the team's time)
+  const bool prof = p.profile != 0 && p.info != nullptr && threadIdx.x == 0;
+  long long t_prev = prof ? clock64() : 0;
+  auto lap = [&](int slot) {
+    if (prof) {
+      const long long t = clock64();
+      p.info[2 + slot + (WARP ? 4 : 0)] += (double)(t - t_prev);
+      t_prev = t;
+    }
+  };
+  while (true) {
+    if (down && !WARP && l == p.warp_start) {  // hand the rest of the hierarchy to warp 0
+      if (threadIdx.x < 32) run_cycle<T, TC, true>(p, sm, red, l);
+      __syncthreads();
+      if (prof) t_prev = clock64();  // the warp team booked its own time
+      if (l == lstart) return;
+      l -= 1;
+      down = false;
+      continue;
+    }
+    if (l == last) {
+      if (WARP) coarse_solve_warp<TC>(uc, fc, p.nx[l], p.ny[l], p.scc, p.hxhy_c, p.ctol, p.xthr, p.exact5, p.cmaxit, p.info);
+      else coarse_solve<TC>(uc, fc, p.nx[l], p.ny[l], p.scc, p.hxhy_c, p.ctol, p.xthr, p.exact5, p.cmaxit, red, p.info);
+      lap(3);
+      if (l == lstart) return;
+      l -= 1;
+      down = false;
+      continue;
+    }
+    if (down) {
+      smooth<T, WARP>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.pre, iso1);
+      lap(0);
+      const int nxc = p.nx[l + 1], nyc = p.ny[l + 1];
+      const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nth = WARP ? 32 : THREADS;
+      if (l + 1 == last) {
+        restrict_residual<T, TC, WARP>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], fc, nxc, nyc, iso1);
+        for (int k = tid; k < nxc * nyc; k += nth) uc[k] = (TC)0;
+      } else {
+        restrict_residual<T, T, WARP>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], F(l + 1), nxc, nyc, iso1);
+        for (int k = tid; k < nxc * nyc; k += nth) U(l + 1)[k] = (T)0;
+      }
+      team_sync<WARP>();
+      lap(1);
+      rep[l] = 0;
+      l += 1;
+    } else {  // a child cycle on level l+1 has just finished
+      rep[l] += 1;
+      const int reps = p.cycle == 0 ? 1 : (p.cycle == 1 ? 2 : max(1, 1 << max(0, L - l - 2)));
+      if (rep[l] < reps) {
+        l += 1;
+        down = true;
+        continue;
+      }
+      if (l + 1 == last) prolong_add<T, TC, WARP>(U(l), p.nx[l], p.ny[l], uc, p.ny[l + 1]);
+      else prolong_add<T, T, WARP>(U(l), p.nx[l], p.ny[l], U(l + 1), p.ny[l + 1]);
+      lap(2);
+      smooth<T, WARP>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.post, iso1);
+      lap(0);
+      if (l == lstart) return;
+      l -= 1;
+    }
+  }
+}
+
 template <typename T, typename TC>
 __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC> p) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -200,6 +502,7 @@ __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC
   TC* const uc = reinterpret_cast<TC*>(sm + p.off_u[last]);
   TC* const fc = reinterpret_cast<TC*>(sm + p.off_f[last]);
 
+  const long long t_begin = clock64();
   // entry level: global -> shared
   {
     const int nx = p.nx[0], ny = p.ny[0];
@@ -213,48 +516,10 @@ __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC
     __syncthreads();
   }
 
-  if (L == 1) {
-    coarse_solve<TC>(uc, fc, p.nx[0], p.ny[0], p.scc, p.hxhy_c, p.ctol, p.cmaxit, red, p.info);
-  } else {
-    int rep[MAXLEV];
-    int l = 0;
-    bool down = true;
-    while (true) {
-      if (l == last) {
-        coarse_solve<TC>(uc, fc, p.nx[l], p.ny[l], p.scc, p.hxhy_c, p.ctol, p.cmaxit, red, p.info);
-        l -= 1;
-        down = false;
-        continue;
-      }
-      if (down) {
-        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.pre, p.iso1 != 0);
-        const int nxc = p.nx[l + 1], nyc = p.ny[l + 1];
-        if (l + 1 == last) {
-          restrict_residual<T, TC>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], fc, nxc, nyc, p.iso1 != 0);
-          for (int k = threadIdx.x; k < nxc * nyc; k += THREADS) uc[k] = (TC)0;
-        } else {
-          restrict_residual<T, T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], F(l + 1), nxc, nyc, p.iso1 != 0);
-          for (int k = threadIdx.x; k < nxc * nyc; k += THREADS) U(l + 1)[k] = (T)0;
-        }
-        __syncthreads();
-        rep[l] = 0;
-        l += 1;
-      } else {  // a child cycle on level l+1 has just finished
-        rep[l] += 1;
-        const int reps = p.cycle == 0 ? 1 : (p.cycle == 1 ? 2 : max(1, 1 << max(0, L - l - 2)));
-        if (rep[l] < reps) {
-          l += 1;
-          down = true;
-          continue;
-        }
-        if (l + 1 == last) prolong_add<T, TC>(U(l), p.nx[l], p.ny[l], uc, p.ny[l + 1]);
-        else prolong_add<T, T>(U(l), p.nx[l], p.ny[l], U(l + 1), p.ny[l + 1]);
-        smooth<T>(U(l), F(l), p.nx[l], p.ny[l], p.sc[l], p.post, p.iso1 != 0);
-        if (l == 0) break;
-        l -= 1;
-      }
-    }
-  }
+  const long long t_loaded = clock64();
+  run_cycle<T, TC, false>(p, sm, red, 0);
+  __syncthreads();
+  const long long t_cycled = clock64();
 
   // entry level: shared -> global (boundary included: the correction may have touched it, multigrid.py:329)
   {
@@ -263,6 +528,12 @@ __global__ void __launch_bounds__(THREADS) small_cycle_kernel(const Params<T, TC
       const int i = k / ny, j = k - i * ny;
       p.u[(int64_t)i * p.ld_u + j] = (L == 1) ? (T)uc[k] : U(0)[k];
     }
+  }
+  if (p.profile != 0 && p.info != nullptr && threadIdx.x == 0) {
+    p.info[10] += (double)(t_loaded - t_begin);
+    p.info[11] += (double)(t_cycled - t_loaded);
+    p.info[12] += (double)(clock64() - t_cycled);
+    p.info[13] += 1.0;
   }
 }
 
@@ -293,8 +564,19 @@ static int launch(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t 
     }
   }
   if (off > 200 * 1024) return MG_ERR_UNSUPPORTED;
-  p.nlev = nlev; p.cycle = cycle; p.pre = pre; p.post = post; p.u_zero = u_zero;
+  p.nlev = nlev; p.cycle = cycle; p.pre = pre; p.post = post; p.u_zero = u_zero & 1; p.profile = (u_zero >> 1) & 1;
   p.iso1 = (omega == 1.0 && hx == hy) ? 1 : 0;  // the same selection as mg_stream_api.cu
+  p.warp_start = nlev;
+  for (int l = nlev - 1; l >= 0 && p.nx[l] <= WARP_TEAM_MAX && p.ny[l] <= WARP_TEAM_MAX; --l) p.warp_start = l;
+  p.exact5 = (p.nx[nlev - 1] == 5 && p.ny[nlev - 1] == 5 && p.scc.recip_exact && p.scc.hx2 == p.scc.hy2 &&
+              p.scc.shift == (TC)0 && p.scc.coeff == (TC)-1) ? 1 : 0;
+  p.xthr = -1.0;  // ctol <= 0: never
+  if (ctol > 0) {
+    double y = ctol * ctol;
+    while (y > 0 && sqrt(y) >= ctol) y = nextafter(y, 0.0);
+    while (sqrt(nextafter(y, INFINITY)) < ctol) y = nextafter(y, INFINITY);
+    p.xthr = (sqrt(y) < ctol) ? y : -1.0;
+  }
   p.ctol = ctol; p.cmaxit = cmaxit; p.u = (T*)u; p.f = (const T*)f; p.ld_u = ld_u; p.ld_f = ld_f; p.info = info;
   auto kern = small_cycle_kernel<T, TC>;
   static bool configured[64] = {false};

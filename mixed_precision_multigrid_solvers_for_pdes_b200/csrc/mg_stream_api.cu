@@ -104,6 +104,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   if (back == BACK_RESID && (!resid_out || ld_ro < ny || dtype != MG_F64)) return MG_ERR_BADARG;
   const bool norm = back == BACK_NORM || back == BACK_RESID;
   if (norm && (!sumsq_out || !workspace)) return MG_ERR_BADARG;
+  // mg_vc_workspace_doubles sizes the partials for tiles of >= 8 rows: a smaller override would overrun it
+  if (norm && rows_override > 0 && rows_override < 8) return MG_ERR_BADARG;
   const size_t esz = dtype == MG_F64 ? 8 : 4;
   auto misaligned = [&](const void* p, int64_t ld, size_t es) {
     return p && (((uintptr_t)p & 15u) || (ld % (int64_t)(16 / es)));
@@ -203,7 +205,8 @@ int mg_vc_defect_pass_slab(const void* u_in, void* u_out, const void* f, const v
                            int norm_row_lo, int norm_row_hi, double shift, void* stream) {
   const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
   const int back = r_out ? BACK_RESID : BACK_NONE;
-  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_U_ZERO);
+  // MG_VC_U_ZERO is honoured: the first defect passes of a solve from u = 0 neither read nor memset the iterate
+  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM);
   if (!e_in) fl |= MG_VC_NO_STORE;
   return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
                   workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,
@@ -215,7 +218,7 @@ int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* 
                       int64_t ld_r, double hx, double hy, double coefficient, int flags, void* stream) {
   const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
   const int back = r_out ? BACK_RESID : BACK_NONE;
-  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM | MG_VC_U_ZERO);
+  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM);
   if (!e_in) fl |= MG_VC_NO_STORE;  // nothing to add: u is unchanged, only the residual is produced
   return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
                   workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,

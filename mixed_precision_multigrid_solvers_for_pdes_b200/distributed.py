@@ -143,11 +143,29 @@ class DeviceBackend:
     def scalar(self, n=1):
         return torch.zeros(n, dtype=torch.float64, device=self.device)
 
-    def vc_pass(self, *a, **k):
-        return self.ops.vc_pass(*a, loader=self.loader, **k)
+    def _workspace(self, f):
+        """Reduction scratch of the norm passes, owned by this back end (= by one solver); grow-only, outgrown
+        buffers stay alive because captured CUDA graphs reference them."""
+        need = self.ops.vc_workspace_doubles(f.shape[0], f.shape[1])
+        w = getattr(self, "_ws", None)
+        if w is None or w.numel() < need:
+            if w is not None:
+                self._ws_retired = getattr(self, "_ws_retired", []) + [w]
+            w = self._ws = torch.zeros(need, dtype=torch.float64, device=self.device)
+        return w
 
-    def vc_defect_pass(self, *a, **k):
-        return self.ops.vc_defect_pass(*a, loader=self.loader, **k)
+    def vc_pass(self, u_in, u_out, f, *a, **k):
+        if k.get("sumsq_out") is not None:
+            k["workspace"] = self._workspace(f)
+        return self.ops.vc_pass(u_in, u_out, f, *a, loader=self.loader, **k)
+
+    def vc_defect_pass(self, u_in, u_out, f, *a, **k):
+        if k.get("r_out") is not None:
+            k["workspace"] = self._workspace(f)
+        return self.ops.vc_defect_pass(u_in, u_out, f, *a, loader=self.loader, **k)
+
+    def zero_ring(self, t, first_row: bool, last_row: bool):
+        self.ops.zero_ring_(t, first_row, last_row)
 
     def sumsq(self, t) -> torch.Tensor:
         """Sum of squares of a (row window of a) pitched field as a 1-element device tensor (no sync)."""
@@ -448,11 +466,13 @@ class DistributedMixedPrecisionSolver:
 
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), precision_strategy: str = "adaptive",
                  switch_threshold: float = 1e-6, tolerance: float = 1e-8, max_iterations: int = 50, backend=None,
-                 device=None, use_cuda_graphs: bool = False, **engine_kw):
+                 device=None, use_cuda_graphs: bool = False, stagnation_ratio: float = 0.95,
+                 stop_on_rounding_floor: bool = True, **engine_kw):
         self.eng = DistributedCycleEngine(nx, ny, domain=domain, backend=backend, device=device, **engine_kw)
         self.mode = {"double": "fp64", "fp64": "fp64", "single": "fp32", "fp32": "fp32", "refinement": "refine"}.get(
             precision_strategy, "switch")
         self.switch_threshold, self.tolerance, self.max_iterations = switch_threshold, tolerance, max_iterations
+        self.stagnation_ratio, self.stop_on_rounding_floor = stagnation_ratio, stop_on_rounding_floor
         s0 = self.eng.part.slab(0)
         self.s0 = s0
         self.hxhy = s0.hx * s0.hy
@@ -490,6 +510,10 @@ class DistributedMixedPrecisionSolver:
     def zero_boundary_ring_of_rhs(self) -> None:
         b = self.eng.bufs(0, torch.float64)
         s = self.s0
+        zr = getattr(self.eng.be, "zero_ring", None)
+        if zr is not None:
+            zr(b.f, s.own_lo == 0, s.own_hi == s.nx_glob)
+            return
         b.f[:, 0] = 0
         b.f[:, -1] = 0
         if s.own_lo == 0:
@@ -498,86 +522,110 @@ class DistributedMixedPrecisionSolver:
             b.f[-1, :] = 0
 
     # -- solve loop ----------------------------------------------------------------------------------------------
+    def _iterate_norm(self, phase: str = "fp64") -> float:
+        """Global h-scaled L2 norm of the current iterate (collective: every rank calls it at the same cycle, which
+        the policy guarantees because all ranks see the same all-reduced residual norms)."""
+        eng = self.eng
+        dt = torch.float32 if phase == "fp32" else torch.float64
+        lo, hi = self.s0.own_local
+        ss = eng.allreduce_sum(eng.be.sumsq(eng.bufs(0, dt).u[lo:hi]))
+        return float(np.sqrt(self.hxhy * float(ss.item())))
+
     def restart(self, keep_iterate: bool = False) -> float:
-        """Begin a solve from u = 0, or (keep_iterate) from whatever the fp64 level-0 iterate holds."""
+        """Begin a solve from u = 0 (the iterate is then neither memset nor read: the first passes carry the U_ZERO
+        flag), or (keep_iterate) from whatever the fp64 level-0 iterate holds."""
+        from .solvers.policy import CyclePolicy, weak_method
         eng = self.eng
         b64 = eng.bufs(0, torch.float64)
-        if not keep_iterate:
-            b64.u.zero_()
-            eng.set_valid(b64.u, eng.part.ghost)
-        self.phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
-        self.history: List[float] = []
+        self._fresh = not keep_iterate
+        self.policy = CyclePolicy(self.mode, self.tolerance, self.switch_threshold, self.s0.hx, self.s0.hy, eng.shift,
+                                  stagnation_ratio=self.stagnation_ratio, stop_on_floor=self.stop_on_rounding_floor,
+                                  u_norm=weak_method(self._iterate_norm))
+        self.phase = self.policy.phase
+        self.history = self.policy.history
+        self.last_action = None
         if self.phase == "refine":
-            return self._defect(with_update=False)
+            return self._defect(with_update=False, u_zero=self._fresh)
         if self.phase == "fp32":
             b32 = eng.bufs(0, torch.float32)
             b32.f.copy_(b64.f)
-            b32.u.copy_(b64.u)
             eng.set_valid(b32.f, eng.vdepth(b64.f))
-            eng.set_valid(b32.u, eng.vdepth(b64.u))
+            if not self._fresh:
+                b32.u.copy_(b64.u)
+                eng.set_valid(b32.u, eng.vdepth(b64.u))
         return float("nan")
 
     def _norm(self, slot: int) -> float:
         return float(np.sqrt(self.hxhy * self.ss[slot].item()))
 
-    def _defect(self, with_update: bool) -> float:
-        self.graphs.run("defect_u" if with_update else "defect", lambda: self._launch_defect(with_update))
+    def _defect(self, with_update: bool, u_zero: bool = False) -> float:
+        self.graphs.run(("defect_u" if with_update else "defect") + ("0" if u_zero else ""),
+                        lambda: self._launch_defect(with_update, u_zero))
         return self._norm(1)
 
-    def _launch_defect(self, with_update: bool) -> None:
+    def _launch_defect(self, with_update: bool, u_zero: bool = False) -> None:
         eng, s = self.eng, self.s0
         b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
+        kw = dict(eng._kw)
+        if u_zero:
+            kw["u_zero"] = True
         self.ss.zero_()
+        G = eng.part.ghost
         if with_update:
-            eng.ensure(1, [(b64.u, 0), (b32.u, 0), (b64.f, 0)])
-            v = min(eng.vdepth(b64.u), eng.vdepth(b32.u))
+            eng.ensure(1, [(b32.u, 0), (b64.f, 0)] + ([] if u_zero else [(b64.u, 0)]))
+            v = min(G if u_zero else eng.vdepth(b64.u), eng.vdepth(b32.u))
             eng.be.vc_defect_pass(b64.u, b64.tmp, b64.f, s.hx, s.hy, e_in=b32.u, r_out=b32.f, sumsq_out=self.ss[1:2],
-                                  norm_rows=s.own_local, **eng._kw)
+                                  norm_rows=s.own_local, **kw)
             b64.u, b64.tmp = b64.tmp, b64.u
             eng.set_valid(b64.u, v)
         else:
-            eng.ensure(1, [(b64.u, 0), (b64.f, 0)])
-            v = eng.vdepth(b64.u)
+            eng.ensure(1, [(b64.f, 0)] + ([] if u_zero else [(b64.u, 0)]))
+            v = G if u_zero else eng.vdepth(b64.u)
             eng.be.vc_defect_pass(b64.u, None, b64.f, s.hx, s.hy, r_out=b32.f, sumsq_out=self.ss[1:2],
-                                  norm_rows=s.own_local, **eng._kw)
+                                  norm_rows=s.own_local, **kw)
         eng.set_valid(b32.f, min(v, eng.vdepth(b64.f)) - 1)
         eng.allreduce_sum(self.ss)
 
-    def _launch_refine(self) -> None:
+    def _launch_refine(self, u_zero: bool = False) -> None:
         self.eng.cycle(torch.float32, 0, u_zero=True)
-        self._launch_defect(True)
+        self._launch_defect(True, u_zero)
 
-    def _launch_uniform(self, dt) -> None:
+    def _launch_uniform(self, dt, u_zero: bool = False) -> None:
         self.ss.zero_()
-        self.eng.cycle(dt, 0, u_zero=False, sumsq_out=self.ss[0:1])
+        self.eng.cycle(dt, 0, u_zero=u_zero, sumsq_out=self.ss[0:1])
         self.eng.allreduce_sum(self.ss)
 
     def step(self) -> float:
+        """One cycle of the solve loop; returns the global h-scaled residual norm.  `self.last_action` says what
+        the policy (solvers/policy.py) made of it: 'continue', 'converged' or 'rounding_floor'."""
+        first = self._fresh and not self.history
         if self.phase == "refine":
-            self.graphs.run("refine", self._launch_refine)
+            self.graphs.run("refine0" if first else "refine", lambda: self._launch_refine(first))
             norm = self._norm(1)
         else:
             dt = torch.float64 if self.phase == "fp64" else torch.float32
-            self.graphs.run(self.phase, lambda: self._launch_uniform(dt))
+            self.graphs.run(self.phase + ("0" if first else ""), lambda: self._launch_uniform(dt, first))
             norm = self._norm(0)
-        self.history.append(norm)
-        if self.phase == "refine" and self.mode == "switch" and self.tolerance <= norm <= self.switch_threshold:
-            self.precision_switches.append({"iteration": len(self.history), "residual": norm, "to": "float64"})
-            self.phase = "fp64"
+        self.last_action = self.policy.observe(norm)
+        self.phase = self.policy.phase
+        self.precision_switches = self.policy.switches
         return norm
 
     def solve(self, keep_iterate: bool = False):
+        from .solvers.policy import CONTINUE, CONVERGED
         self.precision_switches = []
         r0 = self.restart(keep_iterate)
         converged = False
         for _ in range(self.max_iterations):
-            if self.step() < self.tolerance:
-                converged = True
+            self.step()
+            if self.last_action != CONTINUE:
+                converged = self.last_action == CONVERGED  # the reference's meaning; see `stopped_on` otherwise
                 break
         dt = torch.float32 if self.mode == "fp32" else torch.float64
         u = self.eng.bufs(0, dt).u
         return u, {"converged": converged, "iterations": len(self.history), "residual_history": list(self.history),
                    "final_residual": self.history[-1], "initial_residual": r0,
+                   "stopped_on": self.policy.stopped_on, "attainable_residual": self.policy.floor_bound,
                    "precision_switches": list(self.precision_switches), "dist_levels": self.eng.D,
                    "num_levels": self.eng.num_levels, "halo_exchanges": self.eng.exchanges}
 
@@ -757,7 +805,8 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     else:
         nx, ny = world * (n - 1) + 1, n
         domain = (0.0, float(world), 0.0, 1.0)  # square cells, h = 1/(n-1): same spacing as the 1-GPU workload
-    tol = a.tolerance if a.tolerance is not None else (1e-8 if n <= 4097 else 1e-7)
+    tol = a.tolerance if a.tolerance is not None else 1e-8  # the reference's; unattainable sizes end on the rounding floor
+    parity = _bench_parity_check(a, world, rank, dev)  # N-GPU == 1-GPU evidence in the SCALE line (untimed)
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
                                           device=dev, use_cuda_graphs=not a.no_graphs,
@@ -769,9 +818,10 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     state = {"solves": 0, "cycles": [], "last": None}
 
     def step():
-        norm = sol.step()
-        if norm < tol or len(sol.history) >= 30:
+        sol.step()
+        if sol.last_action != "continue" or len(sol.history) >= 30:
             state["solves"] += 1
+            state["stopped_on"] = sol.policy.stopped_on
             state["cycles"].append(len(sol.history))
             state["last"] = list(sol.history)
             sol.restart()
@@ -788,11 +838,15 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     with ClockSampler(dev.index) as clk:
         torch.cuda.synchronize()
         dist.barrier()
+        if hasattr(clk, "mark"):
+            clk.mark(0)
         e0.record()
         for _ in range(a.steps):
             step()
         e1.record()
         torch.cuda.synchronize()
+        if hasattr(clk, "mark"):
+            clk.mark(1)
         dist.barrier()
     ms_local = e0.elapsed_time(e1)
     ex_per_step = (sol.eng.exchanges - ex0) / max(1, a.steps)
@@ -876,10 +930,46 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                    "cuda_graphs": (not a.no_graphs),
                    "graphs_captured": sol.graphs.captured, "priming_solves": primed,
                    "l2": "slab arrays (>= 1 GB) exceed the 126 MB L2; no flush needed",
-                   "cycles_per_solve": state["cycles"][-3:], "last_residual_history": state["last"]},
+                   "cycles_per_solve": state["cycles"][-3:], "last_residual_history": state["last"],
+                   "stopped_on": state.get("stopped_on"), "parity": parity},
         "roofline": roof, "kernels": kernels, "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks,
     }
+
+
+def _bench_parity_check(a, world: int, rank: int, dev, n: int = 4097) -> Dict[str, Any]:
+    """Driver-visible evidence that N GPUs compute what one GPU computes (SURVEY 8e acceptance): the same n x n problem
+    (same strategy and cycle type as the benchmark) is solved on the row slabs of all ranks and by the single-GPU
+    solver on rank 0; owned rows must agree bit for bit, cycle counts must be equal.  Runs before the timed region."""
+    from . import ops
+    from .problems import PoissonProblem
+    from .solvers.mixed_precision import MixedPrecisionMultigrid
+    from .device import empty_field
+    while (n - 1) % (world * 64) != 0:
+        n = 2 * (n - 1) + 1
+    f = empty_field(n, n, torch.float64, dev)
+    ops.fill_sinsin_(f, (0.0, 1.0, 0.0, 1.0), 2 * math.pi ** 2, 1.0, 1.0)
+    ops.zero_ring_(f)
+    dsol = DistributedMixedPrecisionSolver(n, n, precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
+                                           cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader), device=dev,
+                                           use_cuda_graphs=False, **_halo_kw(a, dev))
+    dsol.set_rhs_from_global(f)
+    u, info = dsol.solve()
+    full = dsol.eng.gather_solution(u)
+    out: Dict[str, Any] = {"grid": [n, n], "cycles_distributed": info["iterations"], "dist_levels": dsol.eng.D}
+    if rank == 0:
+        single = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
+                                         cycle_type=a.cycle, loader=a.loader, device=dev, strict_reference_norm=True)
+        us, si = single.solve(PoissonProblem(rhs=f, nx=n, ny=n))
+        hd, hs = info["residual_history"], si["residual_history"]
+        out.update({"cycles_single": si["iterations"], "cycles_equal": si["iterations"] == info["iterations"],
+                    "max_abs_diff": float((full - us).abs().max().item()),
+                    "history_max_rel_diff": max(abs(x - y) / y for x, y in zip(hd, hs)) if len(hd) == len(hs) else None})
+        del single, us
+    del dsol, u, full, f
+    torch.cuda.synchronize()
+    dist.barrier()
+    return out
 
 
 def _halo_kw(a, dev) -> Dict[str, Any]:

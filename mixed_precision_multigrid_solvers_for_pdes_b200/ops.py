@@ -175,6 +175,22 @@ def axpy_(alpha: float, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def zero_(x: torch.Tensor) -> torch.Tensor:
+    """x = 0 over the whole pitched extent of the field (mg_zero: one memset node, no fill kernel)."""
+    nx = x.shape[0]
+    _lib.call("mg_zero", x.data_ptr(), nx, ld(x), code(x.dtype), stream_ptr())
+    return x
+
+
+def zero_ring_(x: torch.Tensor, first_row: bool = True, last_row: bool = True) -> torch.Tensor:
+    """Zero the first / last column and (optionally: a row slab only owns them on the physical boundary) the first /
+    last row of a field, in one launch."""
+    nx, ny = x.shape
+    _lib.call("mg_zero_ring", x.data_ptr(), nx, ny, ld(x), 1 if first_row else 0, 1 if last_row else 0, code(x.dtype),
+              stream_ptr())
+    return x
+
+
 def fill_sinsin_(f: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float = 1.0, kx: float = 1.0,
                  ky: float = 1.0) -> torch.Tensor:
     nx, ny = f.shape
@@ -199,13 +215,24 @@ def maxerr_sinsin(u: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float
 # Fused / temporally blocked passes (mg_vc_* family)
 # ------------------------------------------------------------------------------------------------
 _vc_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+_vc_ws_retired: list = []  # outgrown scratch buffers: never freed, a captured CUDA graph may still write to them
+
+
+def vc_workspace_doubles(nx: int, ny: int) -> int:
+    return _lib.call("mg_vc_workspace_doubles", nx, ny)
 
 
 def _vc_workspace(dev: torch.device, nx: int, ny: int) -> torch.Tensor:
-    need = _lib.call("mg_vc_workspace_doubles", nx, ny)
-    key = (dev.index if dev.index is not None else torch.cuda.current_device(), 0)
+    """Default reduction scratch of the fused passes for callers that do not bring their own (`workspace=`):
+    one per (device, stream), grow-only.  A buffer that has been outgrown is retired, not freed -- CUDA graphs
+    captured earlier have its address baked into their norm passes.  Solver objects own their scratch
+    (CycleEngine.workspace), so two solvers never share partials."""
+    need = vc_workspace_doubles(nx, ny)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
     w = _vc_ws.get(key)
     if w is None or w.numel() < need:
+        if w is not None:
+            _vc_ws_retired.append(w)
         w = torch.zeros(need, dtype=torch.float64, device=dev)
         _vc_ws[key] = w
     return w
@@ -251,7 +278,7 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
             sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
             u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0,
-            smoother: str = "rbgs") -> None:
+            smoother: str = "rbgs", workspace: Optional[torch.Tensor] = None) -> None:
     """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS (``smoother="jacobi"``: damped Jacobi) sweeps ->
     [coarse_out = R(f - A u)] or [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None:
     nothing stored).  ``u_zero``: treat u_in as identically zero without reading it."""
@@ -272,7 +299,11 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
     if u_zero:
         flags |= _lib.VC_U_ZERO
     flags |= _loader_flag(loader)
-    ws = _vc_workspace(f.device, nx, ny) if sumsq_out is not None else None
+    ws = None
+    if sumsq_out is not None:
+        ws = workspace if workspace is not None else _vc_workspace(f.device, nx, ny)
+        if ws.numel() < vc_workspace_doubles(nx, ny):
+            raise ValueError("vc_pass: workspace too small for this grid (see vc_workspace_doubles)")
     timed = TIMER is not None and nx * ny >= TIMER.min_points
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -305,7 +336,8 @@ def _loader_flag(loader: str) -> int:
 def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
                    e_in: Optional[torch.Tensor] = None, r_out: Optional[torch.Tensor] = None,
                    sumsq_out: Optional[torch.Tensor] = None, coefficient: float = -1.0, loader: str = "tma",
-                   rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0) -> None:
+                   rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0,
+                   workspace: Optional[torch.Tensor] = None, u_zero: bool = False) -> None:
     """Mixed-precision defect-correction pass on the fp64 iterate (one HBM pass):
     u_out = u_in + e_in (fp32 correction; None: u unchanged, nothing stored), r_out = fp32(f - A u_out),
     sumsq_out[0] = sum of the squared fp64 residual."""
@@ -316,7 +348,13 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
         if t is not None and t.dtype != torch.float32:
             raise TypeError("vc_defect_pass: correction and residual are fp32")
     flags = ((rows & 0xFFF) << 8) | _loader_flag(loader)
-    ws = _vc_workspace(u_in.device, nx, ny) if r_out is not None else None
+    ws = None
+    if r_out is not None:
+        ws = workspace if workspace is not None else _vc_workspace(u_in.device, nx, ny)
+        if ws.numel() < vc_workspace_doubles(nx, ny):
+            raise ValueError("vc_defect_pass: workspace too small for this grid (see vc_workspace_doubles)")
+    if u_zero:
+        flags |= _lib.VC_U_ZERO
     timed = TIMER is not None and nx * ny >= TIMER.min_points
     if timed:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -329,8 +367,8 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
               ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, shift, stream_ptr())
     if timed:
         ev1.record()
-        TIMER.records.append((("update+" if e_in is not None else "") + ("resid32+N" if r_out is not None else "")
-                              + f"/f64/{nx}x{ny}", ev0, ev1))
+        TIMER.records.append((("Z+" if u_zero else "") + ("update+" if e_in is not None else "")
+                              + ("resid32+N" if r_out is not None else "") + f"/f64/{nx}x{ny}", ev0, ev1))
 
 
 SMALL_CYCLE_SMEM_LIMIT = 200 * 1024
@@ -347,11 +385,22 @@ def small_cycle_fits(nx: int, ny: int, nlev: int, dtype, coarse_dtype) -> bool:
 def small_cycle_(u: torch.Tensor, f: torch.Tensor, hx: float, hy: float, *, nlev: int, cycle_type: str = "V",
                  pre: int = 2, post: int = 2, omega: float = 1.0, coefficient: float = -1.0, shift: float = 0.0,
                  coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000, coarse_dtype=None,
-                 u_zero: bool = False, info: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """One complete sub-cycle over `nlev` levels in a single launch (mg_small_cycle), in place on u."""
+                 u_zero: bool = False, info: Optional[torch.Tensor] = None, profile: bool = False) -> torch.Tensor:
+    """One complete sub-cycle over `nlev` levels in a single launch (mg_small_cycle), in place on u.
+    ``profile``: `info` (16 doubles) accumulates SM cycles per phase kind (see include/mgb200.h)."""
+    if profile and (info is None or info.numel() < 16):
+        raise ValueError("small_cycle_(profile=True) needs an info tensor of 16 doubles")
     nx, ny = u.shape
     cd = coarse_dtype if coarse_dtype is not None else u.dtype
+    timed = TIMER is not None and nx * ny >= TIMER.min_points
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.call("mg_small_cycle", u.data_ptr(), f.data_ptr(), nx, ny, ld(u), ld(f), hx, hy, nlev, _CYCLES[cycle_type],
-              pre, post, omega, coefficient, shift, coarse_tolerance, coarse_max_iterations, 1 if u_zero else 0,
+              pre, post, omega, coefficient, shift, coarse_tolerance, coarse_max_iterations,
+              (1 if u_zero else 0) | (2 if profile else 0),
               info.data_ptr() if info is not None else None, code(u.dtype), code(cd), stream_ptr())
+    if timed:
+        ev1.record()
+        TIMER.records.append((f"small{cycle_type}{nlev}/{'f64' if u.dtype == torch.float64 else 'f32'}/{nx}x{ny}", ev0, ev1))
     return u

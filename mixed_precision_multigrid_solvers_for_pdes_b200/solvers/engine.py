@@ -63,6 +63,10 @@ class CycleEngine:
         self.use_small_cycle = use_small_cycle
         self._small_cache: Dict = {}
         self.coarse_info = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        # reduction scratch of the fused norm passes, owned by this engine and alive as long as the CUDA graphs
+        # captured from it (a shared per-device scratch could be outgrown and freed under a captured graph)
+        g0 = self.levels[0].grid
+        self.workspace = torch.zeros(max(8, ops.vc_workspace_doubles(g0.nx, g0.ny)), dtype=torch.float64, device=self.dev)
 
     # -- buffer roles (u / tmp swap on every out-of-place pass) ---------------------------------------
     def buffer_state(self):
@@ -193,7 +197,7 @@ class CycleEngine:
         # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
         n = self.pre
         if u_zero and n == 0:
-            b.u.zero_()  # nothing will overwrite the iterate before it is read
+            ops.zero_(b.u)  # nothing will overwrite the iterate before it is read
             u_zero = False
         while n > 2:
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero, shift=sh, smoother=sk)
@@ -214,14 +218,15 @@ class CycleEngine:
         first = min(n, 2)
         last = (n - first) == 0
         ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, omega=omega, coefficient=coeff, coarse_in=c.u,
-                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh, smoother=sk)
+                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh, smoother=sk, workspace=self.workspace)
         b.u, b.tmp = b.tmp, b.u
         n -= first
         while n > 0:
             k = min(n, 2)
             n -= k
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, omega=omega, coefficient=coeff,
-                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh, smoother=sk)
+                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh, smoother=sk,
+                        workspace=self.workspace)
             b.u, b.tmp = b.tmp, b.u
 
     # -- the recursion ------------------------------------------------------------------------------
@@ -238,14 +243,14 @@ class CycleEngine:
             return False
         if lvl == L - 1:
             if u_zero:
-                b.u.zero_()
+                ops.zero_(b.u)
             self._coarse_solve(lvl, b, precision_manager)
             return False
         if self._fusable(lvl, level_dtypes):
             self._cycle_fused(level_dtypes, lvl, precision_manager, sumsq_out, u_zero)
             return sumsq_out is not None
         if u_zero:
-            b.u.zero_()
+            ops.zero_(b.u)
         if self.pre > 0:
             self._smooth(lvl, b, self.pre)
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])

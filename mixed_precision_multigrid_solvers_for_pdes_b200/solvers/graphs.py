@@ -9,6 +9,7 @@ from __future__ import annotations
 
 from typing import Any, Callable, Dict
 
+import gc
 import os
 
 import torch
@@ -43,8 +44,19 @@ class GraphCache:
         if entry == "warm":  # second visit: capture (capture does not execute), then replay
             before = self.snapshot_fn()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                launch()
+            # No cyclic garbage collection while capturing: collecting a dead solver destroys ITS CUDA graphs
+            # (graph-exec destruction, frees into its private pool), and such calls invalidate a capture in progress
+            # ("operation failed due to a previous error during capture").  torch.cuda.graph() no longer collects on
+            # entry, so do it here, once per capture.
+            gc_was_enabled = gc.isenabled()
+            gc.collect()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g):
+                    launch()
+            finally:
+                if gc_was_enabled:
+                    gc.enable()
             after = self.snapshot_fn()
             self.restore_fn(before)
             entry = self.entries[key] = (g, after)

@@ -38,6 +38,7 @@ from ..operators.laplacian import HelmholtzOperator, LaplacianOperator
 from ..operators.transfer import ProlongationOperator, RestrictionOperator
 from .engine import CycleEngine
 from .graphs import GraphCache
+from .policy import CONTINUE, CONVERGED, CyclePolicy, weak_method
 from .smoothers import GaussSeidelSmoother, JacobiSmoother
 
 _STRATEGIES = {
@@ -58,7 +59,8 @@ class MixedPrecisionMultigrid:
                  stagnation_ratio: float = 0.95, max_grid_size: Optional[int] = None,
                  gpu_memory_fraction: Optional[float] = None, min_precision: Optional[str] = None,
                  strict_reference_norm: bool = False, kernels: str = "auto", loader: str = "tma", device=None,
-                 use_cuda_graphs: bool = True, shift: float = 0.0, fmg: bool = False, verbose: bool = False):
+                 use_cuda_graphs: bool = True, shift: float = 0.0, fmg: bool = False, verbose: bool = False,
+                 stop_on_rounding_floor: bool = True):
         key = str(precision_strategy).lower()
         if key not in _STRATEGIES:
             raise ValueError(f"Unknown precision strategy: {precision_strategy}")
@@ -76,6 +78,9 @@ class MixedPrecisionMultigrid:
         self.smoother_name, self.damping_factor = smoother, damping_factor
         self.coarse_tolerance, self.coarse_max_iterations = coarse_tolerance, coarse_max_iterations
         self.stagnation_ratio = stagnation_ratio
+        # solvers/policy.py: end a solve whose tolerance lies below the rounding floor of the residual evaluation
+        # once the residual has stopped contracting there (16385^2: the reference's 1e-8 is below the fp64 floor)
+        self.stop_on_rounding_floor = stop_on_rounding_floor
         self.max_grid_size, self.gpu_memory_fraction = max_grid_size, gpu_memory_fraction
         self.kernels, self.loader, self.device, self.verbose = kernels, loader, device, verbose
         # The reference's residual equals f on the boundary ring and its norm sums over ALL points
@@ -172,18 +177,18 @@ class MixedPrecisionMultigrid:
         return float(np.sqrt(self._grid.hx * self._grid.hy * ops.read_scalar(ss)))
 
     # -- one cycle in each precision phase -----------------------------------------------------------------
-    def _launch_uniform_cycle(self, dtype) -> None:
+    def _launch_uniform_cycle(self, dtype, u_zero: bool = False) -> None:
         eng = self._engine
-        fused = eng.cycle([dtype] * eng.num_levels, 0, None, sumsq_out=self._sumsq[0:1])
+        fused = eng.cycle([dtype] * eng.num_levels, 0, None, sumsq_out=self._sumsq[0:1], u_zero=u_zero)
         if not fused:
             self._sumsq[0:1].copy_(eng.residual_sumsq_async(dtype))
 
-    def _cycle_fp64(self) -> float:
-        self._graphed("fp64", lambda: self._launch_uniform_cycle(torch.float64))
+    def _cycle_fp64(self, u_zero: bool = False) -> float:
+        self._graphed("fp64_0" if u_zero else "fp64", lambda: self._launch_uniform_cycle(torch.float64, u_zero))
         return self._norm_from(self._sumsq[0:1])
 
-    def _cycle_fp32_only(self) -> float:
-        self._graphed("fp32", lambda: self._launch_uniform_cycle(torch.float32))
+    def _cycle_fp32_only(self, u_zero: bool = False) -> float:
+        self._graphed("fp32_0" if u_zero else "fp32", lambda: self._launch_uniform_cycle(torch.float32, u_zero))
         return self._norm_from(self._sumsq[0:1])
 
     def _inner_dtypes(self):
@@ -193,37 +198,41 @@ class MixedPrecisionMultigrid:
         L = self._engine.num_levels
         return [torch.float32] * (L - 1) + [torch.float64]
 
-    def _refinement_residual(self, with_update: bool = False) -> float:
-        """One HBM pass over the fp64 iterate: [u += e32] ; r32 = fp32(f - A u) ; fp64 h-scaled ||r||."""
-        self._launch_refinement_residual(with_update)
+    def _refinement_residual(self, with_update: bool = False, u_zero: bool = False) -> float:
+        """One HBM pass over the fp64 iterate: [u += e32] ; r32 = fp32(f - A u) ; fp64 h-scaled ||r||.
+        ``u_zero``: the iterate is the zero initial guess and is neither read nor was it memset."""
+        self._launch_refinement_residual(with_update, u_zero)
         return self._norm_from(self._sumsq[1:2])
 
-    def _launch_refinement_residual(self, with_update: bool) -> None:
+    def _launch_refinement_residual(self, with_update: bool, u_zero: bool = False) -> None:
         eng, g = self._engine, self._grid
         b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)
         ss = self._sumsq[1:2]
         if ops.vc_aligned(b64.u, b64.f, b64.tmp, b32.u, b32.f) and eng.kernels != "basic":
             if with_update:
                 ops.vc_defect_pass(b64.u, b64.tmp, b64.f, g.hx, g.hy, e_in=b32.u, r_out=b32.f, sumsq_out=ss,
-                                   loader=eng.loader, shift=self.shift)
+                                   loader=eng.loader, shift=self.shift, workspace=eng.workspace, u_zero=u_zero)
                 b64.u, b64.tmp = b64.tmp, b64.u
             else:
                 ops.vc_defect_pass(b64.u, None, b64.f, g.hx, g.hy, r_out=b32.f, sumsq_out=ss, loader=eng.loader,
-                                   shift=self.shift)
+                                   shift=self.shift, workspace=eng.workspace, u_zero=u_zero)
         else:  # strict basic kernels
+            if u_zero:
+                ops.zero_(b64.u)
             if with_update:
                 ops.axpy_(1.0, b32.u, b64.u)
             ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp, shift=self.shift)
             ss.copy_(ops.sumsq_async(b64.tmp, slot=1))
             ops.cast(b64.tmp, torch.float32, out=b32.f)
 
-    def _launch_refinement_cycle(self) -> None:
+    def _launch_refinement_cycle(self, u_zero: bool = False) -> None:
         self._engine.cycle(self._inner_dtypes(), 0, None, u_zero=True)
-        self._launch_refinement_residual(True)
+        self._launch_refinement_residual(True, u_zero)
 
-    def _cycle_refinement(self) -> float:
-        """One fp32 cycle on A e = r32 (e0 = 0, never read), then u64 += e32 fused with the next residual."""
-        self._graphed("refine", self._launch_refinement_cycle)
+    def _cycle_refinement(self, u_zero: bool = False) -> float:
+        """One fp32 cycle on A e = r32 (e0 = 0, never read), then u64 += e32 fused with the next residual.
+        ``u_zero``: first cycle of a solve from the zero initial guess (u64 = e32, the iterate is not read)."""
+        self._graphed("refine_0" if u_zero else "refine", lambda: self._launch_refinement_cycle(u_zero))
         return self._norm_from(self._sumsq[1:2])
 
     def _fmg_start(self, dtypes) -> None:
@@ -274,10 +283,20 @@ class MixedPrecisionMultigrid:
 
     def _zero_ring(self, f: torch.Tensor) -> None:
         if not self.strict_reference_norm:
-            f[0, :] = 0
-            f[-1, :] = 0
-            f[:, 0] = 0
-            f[:, -1] = 0
+            ops.zero_ring_(f)
+
+    def _iterate_norm(self, phase: str) -> float:
+        """h-scaled L2 norm of the current iterate (one reduction; only the floor test of the policy asks for it)."""
+        eng = self._engine
+        u = eng.levels[0].bufs(torch.float32 if phase == "fp32" else torch.float64).u
+        return float(np.sqrt(self._grid.hx * self._grid.hy * ops.sumsq(u)))
+
+    def make_policy(self) -> CyclePolicy:
+        """The stopping / switching rules of one solve (solvers/policy.py) bound to this solver's grid."""
+        g = self._grid
+        return CyclePolicy(self.mode, self.tolerance, self.switch_threshold, g.hx, g.hy, self.shift,
+                           stagnation_ratio=self.stagnation_ratio, stop_on_floor=self.stop_on_rounding_floor,
+                           u_norm=weak_method(self._iterate_norm))
 
     def _solve_device(self, have_guess: bool):
         """The cycle loop on the right-hand side / iterate already in the fp64 level-0 buffers.  Synchronises only
@@ -286,14 +305,19 @@ class MixedPrecisionMultigrid:
         eng = self._engine
         b64 = eng.levels[0].bufs(torch.float64)
         cur = torch.cuda.current_stream(eng.dev)
-        history: List[float] = []
         precisions: List[str] = []
-        self.precision_switches = []
-        phase = {"fp64": "fp64", "fp32": "fp32"}.get(self.mode, "refine")
+        pol = self.make_policy()
+        phase = pol.phase
+        # a solve from the zero initial guess never reads (or memsets) the level-0 iterate: its first passes carry
+        # the U_ZERO flag instead (saves a 2 GB memset and two 2 GB reads per 16385^2 solve)
+        fresh = not have_guess and not self.fmg
+        if self.fmg and not have_guess:
+            ops.zero_(b64.u)  # the full-multigrid start overwrites it; keep the buffer defined meanwhile
         if phase == "fp32":
             b32 = eng.levels[0].bufs(torch.float32)
             ops.cast(b64.f, torch.float32, out=b32.f)
-            ops.cast(b64.u, torch.float32, out=b32.u)
+            if not fresh:
+                ops.cast(b64.u, torch.float32, out=b32.u)
         converged = False
         iteration = 0
         cur.synchronize()
@@ -307,35 +331,32 @@ class MixedPrecisionMultigrid:
             else:
                 dt = torch.float64 if phase == "fp64" else torch.float32
                 self._fmg_start([dt] * eng.num_levels)
-        pending = self._refinement_residual() if phase == "refine" else None  # ||r(u_0)||
+        pending = self._refinement_residual(u_zero=fresh) if phase == "refine" else None  # ||r(u_0)||
+        names = {"refine": "mixed", "fp64": "float64", "fp32": "float32"}
         for iteration in range(1, self.max_iterations + 1):
+            phase = pol.phase
+            first = fresh and iteration == 1
             if phase == "refine":
-                norm = self._cycle_refinement()  # residual of the new iterate (also next cycle's rhs)
-                precisions.append("mixed")
+                norm = self._cycle_refinement(u_zero=first)  # residual of the new iterate (also next cycle's rhs)
             elif phase == "fp64":
-                norm = self._cycle_fp64()
-                precisions.append("float64")
+                norm = self._cycle_fp64(u_zero=first)
             else:
-                norm = self._cycle_fp32_only()
-                precisions.append("float32")
-            history.append(norm)
+                norm = self._cycle_fp32_only(u_zero=first)
+            precisions.append(names[phase])
             if self.verbose:
                 print(f"cycle {iteration}: ||r|| = {norm:.3e} [{precisions[-1]}]")
-            if norm < self.tolerance:
-                converged = True
+            action = pol.observe(norm)
+            if action != CONTINUE:
+                # `converged` keeps the reference's meaning (norm < tolerance, solvers/base.py:123-143); a solve that
+                # ends on the rounding floor is as converged as the arithmetic allows and says so in `stopped_on`
+                converged = action == CONVERGED
                 break
-            if phase == "refine":
-                stagnating = (len(history) >= 3 and all(history[-k] > self.stagnation_ratio * history[-k - 1]
-                                                        for k in (1, 2)))
-                if (self.mode == "switch" and norm <= self.switch_threshold) or stagnating:
-                    self.precision_switches.append({"iteration": iteration, "residual": norm, "from": "mixed",
-                                                    "to": "float64",
-                                                    "reason": "stagnation" if stagnating else "switch_threshold"})
-                    phase = "fp64"
+        history = pol.history
+        self.precision_switches = list(pol.switches)
         cur.synchronize()
         t_solve = time.perf_counter() - t_cycles
         b64 = eng.levels[0].bufs(torch.float64)
-        if phase == "fp32":
+        if pol.phase == "fp32":
             u_dev = ops.cast(eng.levels[0].bufs(torch.float32).u, torch.float64, out=b64.tmp)
         else:
             u_dev = b64.u
@@ -350,34 +371,76 @@ class MixedPrecisionMultigrid:
             "precision_history": precisions, "precision_levels_used": sorted(set(precisions)),
             "precision_switches": list(self.precision_switches), "precision_strategy": self.precision_strategy,
             "switch_threshold": self.switch_threshold, "fmg": self.fmg, "cycle_type": self.cycle_type,
+            # "tolerance" (the reference's test) or "rounding_floor" (solvers/policy.py: the tolerance lies below what
+            # an fp64 evaluation of f - A u can return on this grid; `attainable_residual` is the bound used)
+            "stopped_on": pol.stopped_on, "attainable_residual": pol.floor_bound,
             "num_levels": eng.num_levels, "grid_hierarchy": [(l.grid.nx, l.grid.ny) for l in eng.levels],
-            "level_timings": {}, "pre_smooth_iterations": self.pre, "post_smooth_iterations": self.post,
+            "level_timings": self.level_timings(), "pre_smooth_iterations": self.pre,
+            "post_smooth_iterations": self.post,
             "unknowns_per_second": nx * ny * iteration / t_solve if t_solve > 0 else 0.0,
         }
         return u_dev, info
 
-    def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None
-              ) -> Tuple[Any, Dict[str, Any]]:
+    def level_timings(self) -> Dict[int, Dict[str, float]]:
+        """Per-level device time of the last `profile_levels()` run, in the reference's shape
+        (multigrid.py:179-182: {level: {smooth_time, restrict_time, prolong_time}}, seconds).  The fused passes do
+        smoothing and a transfer in ONE kernel, so a pass's time is booked under `smooth_time` and the transfer
+        entries stay 0; `passes` counts the launches.  Empty until `profile_levels()` has run: timing every launch
+        needs an event pair around it, which a replayed CUDA graph cannot hold."""
+        return {k: dict(v) for k, v in getattr(self, "_level_timings", {}).items()}
+
+    def profile_levels(self, cycles: int = 1) -> Dict[int, Dict[str, float]]:
+        """Run `cycles` cycles of the current phase eagerly (no graph replay) with a CUDA-event pair around every
+        fused pass and fill `info['level_timings']` of later solves from them."""
+        eng = self._engine
+        shape_level = {(l.grid.nx, l.grid.ny): i for i, l in enumerate(eng.levels)}
+        graphs, self.use_cuda_graphs = self.use_cuda_graphs, False
+        prev, ops.TIMER = ops.TIMER, ops.KernelTimer(min_points=0)
+        try:
+            for _ in range(cycles):
+                if self.mode in ("switch", "refine"):
+                    self._cycle_refinement()
+                elif self.mode == "fp64":
+                    self._cycle_fp64()
+                else:
+                    self._cycle_fp32_only()
+            summ = ops.TIMER.summary()
+        finally:
+            ops.TIMER, self.use_cuda_graphs = prev, graphs
+        out: Dict[int, Dict[str, float]] = {i: {"smooth_time": 0.0, "restrict_time": 0.0, "prolong_time": 0.0, "passes": 0}
+                                           for i in range(eng.num_levels)}
+        for tag, d in summ.items():
+            nxs, nys = tag.rsplit("/", 1)[1].split("x")
+            lvl = shape_level.get((int(nxs), int(nys)))
+            if lvl is not None:
+                out[lvl]["smooth_time"] += d["total_ms"] * 1e-3 / cycles
+                out[lvl]["passes"] += d["launches"] // cycles
+        self._level_timings = out
+        return self.level_timings()
+
+    def solve(self, problem, initial_guess=None, nx: Optional[int] = None, ny: Optional[int] = None,
+              reuse_output: bool = False) -> Tuple[Any, Dict[str, Any]]:
+        """Solve `problem`; returns (solution, info).  Host input (NumPy / callable source) gives a NumPy solution the
+        caller OWNS, like the reference's arrays: it is downloaded through a pinned staging buffer and copied out.
+        ``reuse_output=True`` skips that copy and returns a VIEW of the pinned staging buffer, which the next
+        `solve()` on this solver overwrites (zero-copy hand-over for callers that consume the result at once).
+        A CUDA-tensor right-hand side gives a CUDA tensor (a fresh clone)."""
         t_start = time.perf_counter()
         nx, ny, domain, rhs = self._resolve_grid(problem, nx, ny)
         eng = self._engine
         b64 = eng.levels[0].bufs(torch.float64)
         was_np = self._load_rhs(problem, rhs, domain, b64.f)
         self._zero_ring(b64.f)
-        if initial_guess is None:
-            b64.u.zero_()
-        else:
+        if initial_guess is not None:
             b64.u.copy_(to_device(initial_guess, device=eng.dev, dtype=torch.float64)[0])
         t_setup = time.perf_counter() - t_start
         u_dev, info = self._solve_device(initial_guess is not None)
         if was_np:
-            # device -> pinned host staging (kept across solves; the returned array is a view of it and is
-            # overwritten by the next solve of this solver object)
             if self._pinned_out is None or tuple(self._pinned_out.shape) != (nx, ny):
                 self._pinned_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True)
             self._pinned_out.copy_(u_dev, non_blocking=True)
             torch.cuda.current_stream(eng.dev).synchronize()
-            solution = self._pinned_out.numpy()
+            solution = self._pinned_out.numpy() if reuse_output else self._pinned_out.numpy().copy()
         else:
             solution = u_dev.clone()
         total = time.perf_counter() - t_start
@@ -444,7 +507,6 @@ class MixedPrecisionMultigrid:
             ev.record(cur)
             consumed[slot] = ev
             self._zero_ring(b64.f)
-            b64.u.zero_()
             u_dev, info = self._solve_device(False)
             if drained[slot] is not None:
                 cur.wait_event(drained[slot])

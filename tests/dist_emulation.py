@@ -60,7 +60,7 @@ class OracleBackend:
         return torch.from_numpy(O.apply_laplacian(_np(u), hx, hy, 1.0))
 
     def vc_pass(self, u_in, u_out, f, hx, hy, *, sweeps=2, omega=1.0, coefficient=-1.0, coarse_in=None,
-                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0):
+                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0, workspace=None):
         F = _np(f)
         nx = F.shape[0]
         nxo = nx if nx % 2 == 1 else nx - 1
@@ -81,8 +81,8 @@ class OracleBackend:
                 sumsq_out[0] = float(np.sum(R[lo:hi].astype(np.float64) ** 2))
 
     def vc_defect_pass(self, u_in, u_out, f, hx, hy, *, e_in=None, r_out=None, sumsq_out=None, coefficient=-1.0,
-                       norm_rows=None, rows=0, shift=0.0):
-        U = _np(u_in).copy()
+                       norm_rows=None, rows=0, shift=0.0, workspace=None, u_zero=False):
+        U = np.zeros_like(_np(f)) if u_zero else _np(u_in).copy()
         if e_in is not None:
             U = U + _np(e_in).astype(np.float64)
             u_out.copy_(torch.from_numpy(U))

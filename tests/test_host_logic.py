@@ -68,3 +68,71 @@ def test_operator_validation_messages():
     with pytest.raises(ValueError, match="Cannot prolongate"):
         ProlongationOperator().apply(Grid(5, 5), np.zeros((5, 5)), Grid(11, 11))
     assert LaplacianOperator(2.0).apply_stencil(g, np.ones((9, 9)), 3, 3) == 0.0
+
+
+# ---- solvers/policy.py: the stopping / switching rules every driver shares (pure Python) -----------------------------
+def _policy(mode, **kw):
+    import importlib.util
+    import os
+    # load the module by path: the package __init__ imports torch + the CUDA library, the policy needs neither
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                        "mixed_precision_multigrid_solvers_for_pdes_b200", "solvers", "policy.py")
+    spec = importlib.util.spec_from_file_location("mgb200_policy", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    h = kw.pop("h", 1.0 / 128)
+    args = dict(tolerance=1e-8, switch_threshold=1e-6, hx=h, hy=h)
+    args.update(kw)
+    return mod, mod.CyclePolicy(mode, **args)
+
+
+def test_policy_reference_tolerance_and_switch_threshold():
+    mod, p = _policy("switch", u_norm=lambda ph: 0.5)
+    hist = [7.562e-1, 4.097e-2, 2.219e-3, 1.202e-4, 6.513e-6, 3.528e-7, 1.911e-8, 1.036e-9]  # SURVEY 8c, 129^2
+    phases, actions = [], []
+    for r in hist:
+        phases.append(p.phase)
+        actions.append(p.observe(r))
+    assert actions == [mod.CONTINUE] * 7 + [mod.CONVERGED] and p.stopped_on == "tolerance"
+    assert phases == ["refine"] * 6 + ["fp64"] * 2
+    assert p.switches == [{"iteration": 6, "residual": 3.528e-7, "from": "mixed", "to": "float64",
+                           "reason": "switch_threshold"}]
+    assert p.floor_bound is None  # the iterate norm was never needed
+
+
+def test_policy_rounding_floor_needs_stagnation_and_the_a_priori_bound():
+    # 16385^2: the fp64 floor of f - A u is ~3e-8 > 1e-8; history of the round-1 run + the cycle that detects the floor
+    h = 1.0 / 16384
+    calls = []
+    mod, p = _policy("switch", h=h, u_norm=lambda ph: calls.append(1) or 0.5)
+    hist = [17.87, 1.148, 6.35e-2, 3.44e-3, 1.88e-4, 9.75e-6, 5.68e-7, 2.87e-8, 2.81e-8, 2.83e-8]
+    actions = [p.observe(r) for r in hist]
+    assert actions == [mod.CONTINUE] * 9 + [mod.FLOOR] and p.stopped_on == "rounding_floor"
+    assert len(calls) == 1                                   # one iterate norm, only when the residual stagnated
+    mod, one = _policy("switch", h=h, u_norm=lambda ph: 0.5, floor_confirmations=1)
+    assert [one.observe(r) for r in hist[:9]][-1] == mod.FLOOR
+    assert abs(p.floor_bound - 2.220446049250313e-16 * 4 * 16384 ** 2 * 0.5) < 1e-20 and hist[-1] <= p.floor_bound
+    # a slowly converging solve far ABOVE the bound is not mistaken for the floor
+    mod, q = _policy("fp64", h=1.0 / 128, u_norm=lambda ph: 0.5)
+    assert [q.observe(r) for r in (1.0, 0.7, 0.5, 0.36)] == [mod.CONTINUE] * 4 and q.stopped_on is None
+    # switched off: runs on
+    mod, off = _policy("switch", h=h, u_norm=lambda ph: 0.5, stop_on_floor=False)
+    assert [off.observe(r) for r in hist][-1] == mod.CONTINUE
+    # the fp32-only strategy runs on like the reference's all-fp32 solves
+    mod, single = _policy("fp32", h=1.0 / 128, u_norm=lambda ph: 0.5)
+    assert [single.observe(r) for r in (1.0, 1e-2, 9.6e-4, 9.5e-4, 9.5e-4, 9.5e-4)] == [mod.CONTINUE] * 6
+
+
+def test_policy_stagnating_refinement_is_promoted_then_ends_on_the_floor():
+    mod, p = _policy("refine", h=1.0 / 16384, u_norm=lambda ph: 0.5)
+    # refinement mode never switches on the threshold; two ratios > 0.95 above the floor bound promote to fp64
+    for r in (1.0, 1e-2, 9.9e-3, 9.8e-3):
+        assert p.observe(r) == mod.CONTINUE
+    assert p.phase == "fp64" and p.switches[0]["reason"] == "stagnation"
+    assert p.observe(3e-8) == mod.CONTINUE and p.observe(2.9e-8) == mod.CONTINUE and p.observe(2.9e-8) == mod.FLOOR
+    # ... and a refinement whose fp64 residual already sits on the floor stops without the detour
+    mod, q = _policy("refine", h=1.0 / 16384, u_norm=lambda ph: 0.5)
+    acts = [q.observe(r) for r in (1.0, 1e-3, 3.0e-8, 2.95e-8, 2.9e-8, 2.9e-8)]
+    assert acts[-1] == mod.FLOOR and q.phase == "refine"
+    with __import__("pytest").raises(ValueError):
+        _policy("half")
