@@ -97,7 +97,8 @@ def test_policy_reference_tolerance_and_switch_threshold():
     assert phases == ["refine"] * 6 + ["fp64"] * 2
     assert p.switches == [{"iteration": 6, "residual": 3.528e-7, "from": "mixed", "to": "float64",
                            "reason": "switch_threshold"}]
-    assert p.floor_bound is None  # the iterate norm was never needed
+    assert p.floor_bound == 2.220446049250313e-16 * 4 * 128 ** 2 * 0.5  # evaluated once, at the switch decision
+    assert p.switch_blocked is None                                   # tolerance 1e-8 >> bound 7e-12: switch as documented
 
 
 def test_policy_rounding_floor_needs_stagnation_and_the_a_priori_bound():
@@ -108,10 +109,18 @@ def test_policy_rounding_floor_needs_stagnation_and_the_a_priori_bound():
     hist = [17.87, 1.148, 6.35e-2, 3.44e-3, 1.88e-4, 9.75e-6, 5.68e-7, 2.87e-8, 2.81e-8, 2.83e-8]
     actions = [p.observe(r) for r in hist]
     assert actions == [mod.CONTINUE] * 9 + [mod.FLOOR] and p.stopped_on == "rounding_floor"
-    assert len(calls) == 1                                   # one iterate norm, only when the residual stagnated
+    assert len(calls) == 1                                   # one iterate norm per solve, when the bound is first needed
+    # the tolerance (1e-8) lies below the floor bound (1.2e-7): the solve stays in the refinement, whose smooth-error
+    # contraction survives on the floor (profiles/r02_floor_study_16385.json), instead of switching to fp64 at 1e-6
+    assert p.switches == [] and p.phase == "refine" and p.switch_blocked["iteration"] == 7
+    # ... where the tolerance is attainable the switch happens as documented (4097^2: bound 7.4e-9 < 1e-8)
+    mod, sw = _policy("switch", h=1.0 / 4096, u_norm=lambda ph: 0.5)
+    assert [sw.observe(r) for r in (7.57e-1, 4.1e-2, 2.2e-3, 1.2e-4, 6.5e-6, 3.6e-7, 1.9e-8, 1.1e-9)][-1] == mod.CONVERGED
+    assert sw.switches[0]["iteration"] == 6 and sw.switch_blocked is None
     mod, one = _policy("switch", h=h, u_norm=lambda ph: 0.5, floor_confirmations=1)
     assert [one.observe(r) for r in hist[:9]][-1] == mod.FLOOR
-    assert abs(p.floor_bound - 2.220446049250313e-16 * 4 * 16384 ** 2 * 0.5) < 1e-20 and hist[-1] <= p.floor_bound
+    assert abs(one.floor_bound - 2.220446049250313e-16 * 4 * 16384 ** 2 * 0.5) < 1e-20
+    assert hist[-1] <= p.floor_bound
     # a slowly converging solve far ABOVE the bound is not mistaken for the floor
     mod, q = _policy("fp64", h=1.0 / 128, u_norm=lambda ph: 0.5)
     assert [q.observe(r) for r in (1.0, 0.7, 0.5, 0.36)] == [mod.CONTINUE] * 4 and q.stopped_on is None
@@ -132,7 +141,7 @@ def test_policy_stagnating_refinement_is_promoted_then_ends_on_the_floor():
     assert p.observe(3e-8) == mod.CONTINUE and p.observe(2.9e-8) == mod.CONTINUE and p.observe(2.9e-8) == mod.FLOOR
     # ... and a refinement whose fp64 residual already sits on the floor stops without the detour
     mod, q = _policy("refine", h=1.0 / 16384, u_norm=lambda ph: 0.5)
-    acts = [q.observe(r) for r in (1.0, 1e-3, 3.0e-8, 2.95e-8, 2.9e-8, 2.9e-8)]
+    acts = [q.observe(r) for r in (1.0, 1e-3, 3.0e-8, 2.95e-8, 2.9e-8)]
     assert acts[-1] == mod.FLOOR and q.phase == "refine"
     with __import__("pytest").raises(ValueError):
         _policy("half")

@@ -25,7 +25,7 @@ def main():
     a = math.pi * h / 2.0
     want = (a / math.sin(a)) ** 2 - 1.0
     rows = []
-    for strategy in ("adaptive", "double"):
+    for strategy in ("adaptive", "refinement", "double"):
         s = MixedPrecisionMultigrid(strategy, switch_threshold=1e-6, tolerance=0.0, stop_on_rounding_floor=False,
                                     max_iterations=cycles)
         s.setup(n, n)
