@@ -626,6 +626,7 @@ class DistributedMixedPrecisionSolver:
         return u, {"converged": converged, "iterations": len(self.history), "residual_history": list(self.history),
                    "final_residual": self.history[-1], "initial_residual": r0,
                    "stopped_on": self.policy.stopped_on, "attainable_residual": self.policy.floor_bound,
+                   "switch_blocked": self.policy.switch_blocked,
                    "precision_switches": list(self.precision_switches), "dist_levels": self.eng.D,
                    "num_levels": self.eng.num_levels, "halo_exchanges": self.eng.exchanges}
 

@@ -374,6 +374,8 @@ class MixedPrecisionMultigrid:
             # "tolerance" (the reference's test) or "rounding_floor" (solvers/policy.py: the tolerance lies below what
             # an fp64 evaluation of f - A u can return on this grid; `attainable_residual` is the bound used)
             "stopped_on": pol.stopped_on, "attainable_residual": pol.floor_bound,
+            # set when the switch to fp64 cycles was skipped because the tolerance lies below the rounding floor
+            "switch_blocked": pol.switch_blocked,
             "num_levels": eng.num_levels, "grid_hierarchy": [(l.grid.nx, l.grid.ny) for l in eng.levels],
             "level_timings": self.level_timings(), "pre_smooth_iterations": self.pre,
             "post_smooth_iterations": self.post,
