@@ -36,7 +36,6 @@ template <typename T, typename TC> struct Params {
   int u_zero;
   int profile;  // 1: info[2..9] += SM cycles spent per phase kind (see mg_small_cycle in mgb200.h); info holds 16 doubles
   int iso1;  // hx == hy and omega == 1: the streaming kernel's 5-instruction point update (same bits as there)
-  int warp_start;  // first level worked on by warp 0 alone (all sides <= WARP_TEAM_MAX); nlev if none
   int exact5;      // coarsest grid is 5 x 5 with dyadic isotropic spacing, no shift, coefficient -1: register solver
   double xthr;     // largest double whose square root is below ctol (exact5 stopping test without a sqrt per sweep)
   T* u;
@@ -61,89 +60,43 @@ __device__ __forceinline__ T resid_at(const T* u, const T* f, int nx, int ny, in
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Teams.  A level is worked on either by the whole block (rows over warps, columns over lanes, __syncthreads
-// between phases) or -- grids of at most 17 x 17 -- by WARP 0 ALONE with __syncwarp between phases: a phase on
-// such a grid is one or two instructions per lane, and a 32-warp barrier costs more than the phase itself.
-// A W-cycle visits these levels thousands of times per fine-grid cycle.
+// Phases.  Every level is worked on by the whole block: rows over warps, columns over lanes, one barrier per phase.
+// Measured on B200 (profiles/r02_small_cycle_profile.json) and kept in mind below:
+//   * on the tiny levels a phase is a handful of instructions per thread, executed ONCE per visit, so its cost is the
+//     instruction fetch of cold straight-line code (~1000 cycles per phase when the body was unrolled four-fold with
+//     grouped loads, ~3x less as a compact loop): the phase functions are small noinline functions with rolled loops,
+//     specialised at compile time (ISO1) instead of carrying both point updates;
+//   * handing the 9 x 9 and 17 x 17 levels to ONE warp (no block barrier) lost: a single warp walks 2-4 row groups per
+//     half-sweep where 16 warps take one row each; only the 5 x 5 coarsest solve runs in one thread;
+//   * on the large levels (129^2, 65^2) a half-sweep is bound by shared-memory bandwidth (stride-2 red-black accesses
+//     use half of every 128-byte wavefront).
 // ---------------------------------------------------------------------------------------------------------
-template <bool WARP> __device__ __forceinline__ void team_sync() {
-  if (WARP) __syncwarp();
-  else __syncthreads();
-}
-constexpr int WARP_TEAM_MAX = 17;  // largest side of a level handled by the warp team
-
-template <typename T>
-__device__ __forceinline__ T relax_pt(const StencilScalars<T>& s, bool iso1, T uc, T up, T dn, T rt, T lf, T fv) {
-  return iso1 ? relax_iso1<T>(s, up, dn, rt, lf, fv) : relax_fast<T>(s, uc, up, dn, rt, lf, fv);
-}
-
-// log2 of the smallest power of two >= n (n <= 32)
-__device__ __forceinline__ int log2_ceil32(int n) { return n <= 1 ? 0 : (n <= 2 ? 1 : (n <= 4 ? 2 : (n <= 8 ? 3 : (n <= 16 ? 4 : 5)))); }
-
-// Red-black sweeps.  The points of one colour depend only on the other colour, so a thread first LOADS the stencils of
-// all its points of a group, then computes and stores them: the loads of a group are in flight together instead of one
-// shared-memory round trip per point (the loop-carried store otherwise serialises them: measured 600 cycles per
-// half-sweep on 17 x 17 with one warp, 3500 on 129 x 129 with the block).
-template <typename T, bool WARP>
-__device__ __noinline__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>* sp, int sweeps, bool iso1) {
-  const StencilScalars<T> s = *sp;  // from shared memory into registers
+template <typename T, bool ISO1>
+__device__ __noinline__ void smooth(T* u, const T* f, int nx, int ny, const StencilScalars<T>* sp, int sweeps) {
+  const StencilScalars<T> s = *sp;  // shared memory -> registers (only the fields the chosen update reads)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int GP = 4;  // points per group
-  if (WARP) {
-    // lane = r * W + c: W = power of two >= points of one colour per row, 32 / W rows per step; <= GP steps (sides <= 17)
-    const int wl = log2_ceil32((ny - 1) >> 1);
-    const int r = lane >> wl, c = lane & ((1 << wl) - 1), rstep = 32 >> wl;
-    for (int k = 0; k < sweeps; ++k)
-      for (int col = 0; col < 2; ++col) {
-        T uc[GP], up[GP], dn[GP], rt[GP], lf[GP], fv[GP];
-        int idx[GP];
-#pragma unroll
-        for (int q = 0; q < GP; ++q) {
-          const int i = 1 + r + q * rstep, j = 1 + ((i + 1 + col) & 1) + 2 * c;
-          idx[q] = (i <= nx - 2 && j <= ny - 2) ? i * ny + j : -1;
-          if (idx[q] >= 0) {
-            const T* p = u + idx[q];
-            uc[q] = p[0]; up[q] = p[ny]; dn[q] = p[-ny]; rt[q] = p[1]; lf[q] = p[-1]; fv[q] = f[idx[q]];
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < GP; ++q)
-          if (idx[q] >= 0) u[idx[q]] = relax_pt<T>(s, iso1, uc[q], up[q], dn[q], rt[q], lf[q], fv[q]);
-        __syncwarp();
+#pragma unroll 1
+  for (int h = 0; h < 2 * sweeps; ++h) {  // half-sweeps: red (row + column even) first
+#pragma unroll 1
+    for (int i = 1 + warp; i <= nx - 2; i += THREADS / 32) {
+      T* row = u + i * ny;
+      const T* frow = f + i * ny;
+#pragma unroll 1
+      for (int j = 1 + ((i + 1 + h) & 1) + 2 * lane; j <= ny - 2; j += 64) {
+        T* p = row + j;
+        p[0] = ISO1 ? relax_iso1<T>(s, p[ny], p[-ny], p[1], p[-1], frow[j])
+                    : relax_fast<T>(s, p[0], p[ny], p[-ny], p[1], p[-1], frow[j]);
       }
-    return;
-  }
-  const int nwarps = THREADS / 32;
-  for (int k = 0; k < sweeps; ++k)
-    for (int col = 0; col < 2; ++col) {
-      // rows over warps, columns over lanes; groups of GP rows per thread
-      for (int i0 = 1 + warp; i0 <= nx - 2; i0 += GP * nwarps)
-        for (int j0 = 1 + 2 * lane; j0 <= ny - 2; j0 += 64) {
-          T uc[GP], up[GP], dn[GP], rt[GP], lf[GP], fv[GP];
-          int idx[GP];
-#pragma unroll
-          for (int q = 0; q < GP; ++q) {
-            const int i = i0 + q * nwarps, j = j0 + ((i + 1 + col) & 1);
-            idx[q] = (i <= nx - 2 && j <= ny - 2) ? i * ny + j : -1;
-            if (idx[q] >= 0) {
-              const T* p = u + idx[q];
-              uc[q] = p[0]; up[q] = p[ny]; dn[q] = p[-ny]; rt[q] = p[1]; lf[q] = p[-1]; fv[q] = f[idx[q]];
-            }
-          }
-#pragma unroll
-          for (int q = 0; q < GP; ++q)
-            if (idx[q] >= 0) u[idx[q]] = relax_pt<T>(s, iso1, uc[q], up[q], dn[q], rt[q], lf[q], fv[q]);
-        }
-      __syncthreads();
     }
+    __syncthreads();
+  }
 }
 
 // Full weighting of the residual at ONE interior coarse point (I, J) from the 5 x 5 patch of u around fine (2I, 2J): the
 // nine residuals it averages are all at interior fine points (2I - 1 >= 1), so there is no boundary case and 21 + 9 loads
 // replace the 9 x 6 of nine independent residual evaluations.  Reference summation order (transfer.py:116-122).
-template <typename T>
-__device__ __forceinline__ T fw_residual_at(const T* u, const T* f, int ny, int i, int j, const StencilScalars<T>& s,
-                                            bool iso1) {
+template <typename T, bool ISO1>
+__device__ __forceinline__ T fw_residual_at(const T* u, const T* f, int ny, int i, int j, const StencilScalars<T>& s) {
   T w[5][5];
 #pragma unroll
   for (int a = 0; a < 5; ++a)
@@ -156,7 +109,7 @@ __device__ __forceinline__ T fw_residual_at(const T* u, const T* f, int ny, int 
 #pragma unroll
     for (int b = 1; b <= 3; ++b) {
       const T fv = f[(i - 2 + a) * ny + (j - 2 + b)];
-      r[a - 1][b - 1] = iso1 ? residual_iso<T>(s, w[a][b], w[a + 1][b], w[a - 1][b], w[a][b + 1], w[a][b - 1], fv)
+      r[a - 1][b - 1] = ISO1 ? residual_iso<T>(s, w[a][b], w[a + 1][b], w[a - 1][b], w[a][b + 1], w[a][b - 1], fv)
                              : residual_fast<T>(s, w[a][b], w[a + 1][b], w[a - 1][b], w[a][b + 1], w[a][b - 1], fv);
     }
   const T corners = ((r[0][0] + r[0][2]) + r[2][0]) + r[2][2];
@@ -164,49 +117,46 @@ __device__ __forceinline__ T fw_residual_at(const T* u, const T* f, int ny, int 
   return ((T)0.0625 * corners + (T)0.125 * edges) + (T)0.25 * r[1][1];
 }
 
-// f_c = R(f - A u): injection on the coarse boundary, full weighting inside
-template <typename T, typename TO, bool WARP>
+// f_c = R(f - A u): injection on the coarse boundary, full weighting inside; then the coarse iterate is zeroed
+template <typename T, typename TO, bool ISO1>
 __device__ __noinline__ void restrict_residual(const T* u, const T* f, int nx, int ny, const StencilScalars<T>* sp, TO* fc,
-                                               int nxc, int nyc, bool iso1) {
+                                               TO* uc, int nxc, int nyc) {
   const StencilScalars<T> s = *sp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // lanes over (row, column) pairs: W = power of two >= nyc columns, 32 / W rows per warp step
-  const int wl = WARP ? log2_ceil32(nyc) : 5;
-  const int r = WARP ? (lane >> wl) : warp, c = WARP ? (lane & ((1 << wl) - 1)) : lane;
-  const int rstep = WARP ? (32 >> wl) : THREADS / 32, cstep = WARP ? (1 << wl) : 32;
-  for (int I = r; I < nxc; I += rstep)
-    for (int J = c; J < nyc; J += cstep) {
+#pragma unroll 1
+  for (int I = warp; I < nxc; I += THREADS / 32)
+#pragma unroll 1
+    for (int J = lane; J < nyc; J += 32) {
       const int i = 2 * I, j = 2 * J;
       T v;
-      if (I == 0 || I == nxc - 1 || J == 0 || J == nyc - 1) v = resid_at<T>(u, f, nx, ny, i, j, s, iso1);
-      else v = fw_residual_at<T>(u, f, ny, i, j, s, iso1);
+      if (I == 0 || I == nxc - 1 || J == 0 || J == nyc - 1) v = resid_at<T>(u, f, nx, ny, i, j, s, ISO1);
+      else v = fw_residual_at<T, ISO1>(u, f, ny, i, j, s);
       fc[I * nyc + J] = (TO)v;
+      uc[I * nyc + J] = (TO)0;  // the coarse error equation starts from zero (multigrid.py:303)
     }
-  // no barrier here: the caller zeroes the coarse iterate next and synchronises once for both
+  __syncthreads();
 }
 
 // u += P e_c, bilinear with the reference's last-row / last-column treatment (transfer.py:234-267)
-template <typename T, typename TI, bool WARP>
+template <typename T, typename TI>
 __device__ __noinline__ void prolong_add(T* u, int nx, int ny, const TI* ec, int nyc) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wl = WARP ? log2_ceil32(ny) : 5;
-  const int r = WARP ? (lane >> wl) : warp, c0 = WARP ? (lane & ((1 << wl) - 1)) : lane;
-  const int rstep = WARP ? (32 >> wl) : THREADS / 32, cstep = WARP ? (1 << wl) : 32;
-  for (int i = r; i < nx; i += rstep)
-    for (int j = c0; j < ny; j += cstep) {
-      const int idx = i * ny + j;
+#pragma unroll 1
+  for (int i = warp; i < nx; i += THREADS / 32)
+#pragma unroll 1
+    for (int j = lane; j < ny; j += 32) {
       const TI* c = ec + (i >> 1) * nyc + (j >> 1);
       const bool oi = i & 1, oj = j & 1;
-      // all four coarse neighbours, clamped into the array (unused ones are multiplied out below): no divergent loads
+      // all four coarse neighbours, clamped into the array (unused ones drop out below): no divergent loads
       const T c00 = (T)c[0], c01 = (T)c[oj ? 1 : 0], c10 = (T)c[oi ? nyc : 0], c11 = (T)c[(oi ? nyc : 0) + (oj ? 1 : 0)];
       T v;
       if (!oi && !oj) v = c00;
       else if (oi && !oj) v = (j < ny - 1) ? (T)0.5 * (c00 + c10) : (T)0;
       else if (!oi && oj) v = (i < nx - 1) ? (T)0.5 * (c00 + c01) : (T)0;
       else v = (T)0.25 * (((c00 + c01) + c10) + c11);
-      u[idx] += v;
+      u[i * ny + j] += v;
     }
-  team_sync<WARP>();
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -328,15 +278,12 @@ __device__ __forceinline__ void coarse_solve_5x5_exact(TC* u, const TC* f, const
   }
 }
 
+// zb: the boundary rings of the coarsest u and f are zero.  Decided ONCE per launch from the entry level (coarse
+// boundary values of f are injected from the entry ring, transfer.py:109-113; coarse iterates start from zero), not
+// per call: the prologue of a coarsest solve is cold straight-line code and a W-cycle runs it thousands of times.
 template <typename TC>
 __device__ __noinline__ void coarse_solve_5x5(TC* u, const TC* f, const Scal5<TC> s, double hxhy, double xthr, int maxit,
-                                              double* info) {
-  bool zb = true;
-#pragma unroll
-  for (int k = 0; k < 25; ++k) {
-    const int i = k / 5, j = k % 5;
-    if (!(i >= 1 && i <= 3 && j >= 1 && j <= 3)) zb = zb && u[k] == (TC)0 && f[k] == (TC)0;
-  }
+                                              double* info, int zb) {
   if (zb) coarse_solve_5x5_exact<TC, true>(u, f, s, hxhy, xthr, maxit, info);
   else coarse_solve_5x5_exact<TC, false>(u, f, s, hxhy, xthr, maxit, info);
 }
@@ -386,8 +333,9 @@ __device__ __forceinline__ void coarse_solve_warp(TC* u, const TC* f, int nx, in
                                                double tol, double xthr, int exact5, int maxit, double* info) {
   const StencilScalars<TC> s = *sp;
   const int lane = threadIdx.x & 31;
-  if (exact5) {  // uniform
-    if (lane == 0) coarse_solve_5x5<TC>(u, f, Scal5<TC>{s.hx2, s.ihx2, s.inv_neg_diag}, hxhy, xthr, maxit, info);
+  if (exact5) {  // uniform; bit 1 = zero boundary rings
+    if (lane == 0)
+      coarse_solve_5x5<TC>(u, f, Scal5<TC>{s.hx2, s.ihx2, s.inv_neg_diag}, hxhy, xthr, maxit, info, exact5 & 2);
     __syncwarp();
     return;
   }
@@ -476,62 +424,43 @@ __device__ __noinline__ void coarse_solve(TC* u, const TC* f, int nx, int ny, co
   __syncthreads();
 }
 
-// The V / W / F recursion of solvers/multigrid.py:253-337 over levels lstart .. L-1, iteratively, by one team.
-// The block team hands the sub-cycle of the levels from p.warp_start on to warp 0 (run_cycle<.., true>) and waits.
-template <typename T, typename TC, bool WARP>
+// The V / W / F recursion of solvers/multigrid.py:253-337 over all levels, iteratively.
+template <typename T, typename TC, bool ISO1>
 __device__ __forceinline__ void run_cycle(const Params<T, TC>& p, unsigned char* sm, double* red,
-                                          const StencilScalars<T>* sc, const StencilScalars<TC>* scc, int lstart) {
+                                          const StencilScalars<T>* sc, const StencilScalars<TC>* scc, int exact5) {
   const int L = p.nlev, last = L - 1;
   auto U = [&](int l) { return reinterpret_cast<T*>(sm + p.off_u[l]); };
   auto F = [&](int l) { return reinterpret_cast<T*>(sm + p.off_f[l]); };
   TC* const uc = reinterpret_cast<TC*>(sm + p.off_u[last]);
   TC* const fc = reinterpret_cast<TC*>(sm + p.off_f[last]);
-  const bool iso1 = p.iso1 != 0;
   int rep[MAXLEV];
-  int l = lstart;
+  int l = 0;
   bool down = true;
-  // optional phase profile (one thread's clock; phases end with a team barrier, so this is the team's time)
+  // optional phase profile (thread 0's clock; every phase ends with a block barrier, so this is the block's time)
   const bool prof = p.profile != 0 && p.info != nullptr && threadIdx.x == 0;
   long long t_prev = prof ? clock64() : 0;
   auto lap = [&](int slot) {
     if (prof) {
       const long long t = clock64();
-      p.info[2 + slot + (WARP ? 4 : 0)] += (double)(t - t_prev);
+      p.info[2 + slot] += (double)(t - t_prev);
       t_prev = t;
     }
   };
   while (true) {
-    if (down && !WARP && l == p.warp_start) {  // hand the rest of the hierarchy to warp 0
-      if (threadIdx.x < 32) run_cycle<T, TC, true>(p, sm, red, sc, scc, l);
-      __syncthreads();
-      if (prof) t_prev = clock64();  // the warp team booked its own time
-      if (l == lstart) return;
-      l -= 1;
-      down = false;
-      continue;
-    }
     if (l == last) {
-      if (WARP) coarse_solve_warp<TC>(uc, fc, p.nx[l], p.ny[l], scc, p.hxhy_c, p.ctol, p.xthr, p.exact5, p.cmaxit, p.info);
-      else coarse_solve<TC>(uc, fc, p.nx[l], p.ny[l], scc, p.hxhy_c, p.ctol, p.xthr, p.exact5, p.cmaxit, red, p.info);
+      coarse_solve<TC>(uc, fc, p.nx[l], p.ny[l], scc, p.hxhy_c, p.ctol, p.xthr, exact5, p.cmaxit, red, p.info);
       lap(3);
-      if (l == lstart) return;
+      if (l == 0) return;
       l -= 1;
       down = false;
       continue;
     }
     if (down) {
-      smooth<T, WARP>(U(l), F(l), p.nx[l], p.ny[l], sc + l, p.pre, iso1);
+      smooth<T, ISO1>(U(l), F(l), p.nx[l], p.ny[l], sc + l, p.pre);
       lap(0);
       const int nxc = p.nx[l + 1], nyc = p.ny[l + 1];
-      const int tid = WARP ? (threadIdx.x & 31) : threadIdx.x, nth = WARP ? 32 : THREADS;
-      if (l + 1 == last) {
-        restrict_residual<T, TC, WARP>(U(l), F(l), p.nx[l], p.ny[l], sc + l, fc, nxc, nyc, iso1);
-        for (int k = tid; k < nxc * nyc; k += nth) uc[k] = (TC)0;
-      } else {
-        restrict_residual<T, T, WARP>(U(l), F(l), p.nx[l], p.ny[l], sc + l, F(l + 1), nxc, nyc, iso1);
-        for (int k = tid; k < nxc * nyc; k += nth) U(l + 1)[k] = (T)0;
-      }
-      team_sync<WARP>();
+      if (l + 1 == last) restrict_residual<T, TC, ISO1>(U(l), F(l), p.nx[l], p.ny[l], sc + l, fc, uc, nxc, nyc);
+      else restrict_residual<T, T, ISO1>(U(l), F(l), p.nx[l], p.ny[l], sc + l, F(l + 1), U(l + 1), nxc, nyc);
       lap(1);
       rep[l] = 0;
       l += 1;
@@ -543,12 +472,12 @@ __device__ __forceinline__ void run_cycle(const Params<T, TC>& p, unsigned char*
         down = true;
         continue;
       }
-      if (l + 1 == last) prolong_add<T, TC, WARP>(U(l), p.nx[l], p.ny[l], uc, p.ny[l + 1]);
-      else prolong_add<T, T, WARP>(U(l), p.nx[l], p.ny[l], U(l + 1), p.ny[l + 1]);
+      if (l + 1 == last) prolong_add<T, TC>(U(l), p.nx[l], p.ny[l], uc, p.ny[l + 1]);
+      else prolong_add<T, T>(U(l), p.nx[l], p.ny[l], U(l + 1), p.ny[l + 1]);
       lap(2);
-      smooth<T, WARP>(U(l), F(l), p.nx[l], p.ny[l], sc + l, p.post, iso1);
+      smooth<T, ISO1>(U(l), F(l), p.nx[l], p.ny[l], sc + l, p.post);
       lap(0);
-      if (l == lstart) return;
+      if (l == 0) return;
       l -= 1;
     }
   }
@@ -571,21 +500,26 @@ __global__ void __launch_bounds__(THREADS, 1) small_cycle_kernel(const Params<T,
   if (threadIdx.x == 32) scc_s = p.scc;
 
   const long long t_begin = clock64();
-  // entry level: global -> shared
+  // entry level: global -> shared; on the way, are the boundary rings of u and f zero?
+  int ring_zero;
   {
     const int nx = p.nx[0], ny = p.ny[0];
+    int ok = 1;
     for (int k = threadIdx.x; k < nx * ny; k += THREADS) {
       const int i = k / ny, j = k - i * ny;
       const T fv = p.f[(int64_t)i * p.ld_f + j];
       const T uv = p.u_zero ? (T)0 : p.u[(int64_t)i * p.ld_u + j];
+      if ((i == 0 || i == nx - 1 || j == 0 || j == ny - 1) && !(fv == (T)0 && uv == (T)0)) ok = 0;
       if (L == 1) { uc[k] = (TC)uv; fc[k] = (TC)fv; }
       else { U(0)[k] = uv; F(0)[k] = fv; }
     }
-    __syncthreads();
+    ring_zero = __syncthreads_and(ok);
   }
 
   const long long t_loaded = clock64();
-  run_cycle<T, TC, false>(p, sm, red, sc_s, &scc_s, 0);
+  const int exact5 = p.exact5 ? (1 | (ring_zero ? 2 : 0)) : 0;
+  if (p.iso1) run_cycle<T, TC, true>(p, sm, red, sc_s, &scc_s, exact5);
+  else run_cycle<T, TC, false>(p, sm, red, sc_s, &scc_s, exact5);
   __syncthreads();
   const long long t_cycled = clock64();
 
@@ -634,8 +568,6 @@ static int launch(void* u, const void* f, int nx, int ny, int64_t ld_u, int64_t 
   if (off > 200 * 1024) return MG_ERR_UNSUPPORTED;
   p.nlev = nlev; p.cycle = cycle; p.pre = pre; p.post = post; p.u_zero = u_zero & 1; p.profile = (u_zero >> 1) & 1;
   p.iso1 = (omega == 1.0 && hx == hy) ? 1 : 0;  // the same selection as mg_stream_api.cu
-  p.warp_start = nlev;
-  for (int l = nlev - 1; l >= 0 && p.nx[l] <= WARP_TEAM_MAX && p.ny[l] <= WARP_TEAM_MAX; --l) p.warp_start = l;
   p.exact5 = (p.nx[nlev - 1] == 5 && p.ny[nlev - 1] == 5 && p.scc.recip_exact && p.scc.hx2 == p.scc.hy2 &&
               p.scc.shift == (TC)0 && p.scc.coeff == (TC)-1) ? 1 : 0;
   p.xthr = -1.0;  // ctol <= 0: never

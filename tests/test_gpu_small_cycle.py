@@ -50,7 +50,8 @@ def test_sub_cycle_on_dyadic_grids_is_bitwise_the_reference_recursion(n, nlev, d
     if dt != cdt:
         # fp32 levels under an fp64 coarsest level: the reference interpolates in the GRID dtype (fp64) and rounds the
         # sum once (transfer.py:236, multigrid.py:329) where the kernel interpolates in fp32 -- fp32 rounding apart
-        assert np.max(np.abs(got - want.astype(dt))) <= 2e-6 * np.max(np.abs(want))
+        # (a W or F cycle revisits the levels and compounds the differences)
+        assert np.max(np.abs(got - want.astype(dt))) <= (2e-6 if cycle == "V" else 2e-4) * np.max(np.abs(want))
         return
     assert np.array_equal(got, want.astype(dt))
     assert int(info[0]) == sweeps[-1]                    # sweep count of the last coarsest solve: same stopping decisions
