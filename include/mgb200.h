@@ -193,6 +193,31 @@ MG_API int mg_varcoef_smooth_rbgs(void* u, const void* f, const void* a, int nx,
                            int64_t ld_f, int64_t ld_a, double hx, double hy, double shift, double omega,
                            int sweeps, int dtype, void* stream);
 
+/* Coarsest-level solve for the variable-coefficient operator: <= max_iterations x [one red-black GS sweep, residual,
+ * h-scaled L2 norm], stop below `tolerance` -- IterativeSolver.solve (solvers/base.py:258-285) with the red-black
+ * variable-coefficient smoother as the solver, in ONE launch (stopping test in the kernel).  Grids up to 65 x 65.
+ * `info` (device, 2 doubles, may be NULL) = {sweeps, last norm}. */
+MG_API int mg_varcoef_coarse_solve(void* u, const void* f, const void* a, int nx, int ny, int64_t ld_u, int64_t ld_f,
+                            int64_t ld_a, double hx, double hy, double shift, double omega, double tolerance,
+                            int max_iterations, double* info, int dtype, void* stream);
+
+/* Fused / temporally blocked passes of the variable-coefficient operator  A u = -div(a grad u) + shift*u  (README.md:175
+ * advertises the problem class, docs/methodology.md:710 the implicit heat system it serves; the reference ships no operator:
+ * SURVEY 8f-1, parity unpinned).  Same pass structure, flags and slab semantics as mg_vc_pass_slab /
+ * mg_vc_defect_pass_slab; `a` = nodal coefficient field of the level (same shape and dtype as u: +1 word per point of
+ * traffic), staged through the same TMA ring.  Red-black GS only, TMA loader only, fp64 passes carry at most one sweep;
+ * MG_VC_PROLONG together with MG_VC_RESTRICT is not instantiated.  On grids with power-of-two spacings the results are
+ * bit-identical to mg_varcoef_smooth_rbgs / mg_varcoef_residual (true division by the per-point diagonal is kept). */
+MG_API int mg_vcv_pass_slab(const void* u_in, void* u_out, const void* f, const void* a, const void* coarse_in,
+                     void* coarse_out, double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in,
+                     int64_t ld_out, int64_t ld_f, int64_t ld_a, int64_t ld_ci, int64_t ld_co, double hx, double hy,
+                     double omega, int sweeps, int dtype, int flags, int norm_row_lo, int norm_row_hi, double shift,
+                     void* stream);
+MG_API int mg_vcv_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* a, const void* e_in,
+                            void* r_out, double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in,
+                            int64_t ld_out, int64_t ld_f, int64_t ld_a, int64_t ld_e, int64_t ld_r, double hx, double hy,
+                            int flags, int norm_row_lo, int norm_row_hi, double shift, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused, temporally blocked V/W-cycle passes ("vector path": TMA-staged, 16-byte aligned fields)
  *

@@ -73,11 +73,12 @@ struct PassParams {
   const void* f;
   const void* coarse_in;   // e_c (FRONT_PROLONG) or null
   void* coarse_out;        // restricted residual (BACK_RESTRICT) or null
+  const void* a;           // nodal diffusion coefficient (VARCOEF kernels; cp.async loader reads it directly) or null
   const float* fine_in;    // fp32 fine-grid correction (FRONT_ADDFINE) or null
   float* resid_out;        // fp32 fine-grid residual (BACK_RESID) or null
   double* partials;        // one double per warp (BACK_NORM / BACK_RESID) or null
   int nx, ny, nxc, nyc;
-  int64_t ld_in, ld_out, ld_f, ld_ci, ld_co, ld_fi, ld_ro;
+  int64_t ld_in, ld_out, ld_f, ld_ci, ld_co, ld_fi, ld_ro, ld_a;
   int u_zero;              // 1: u_in is identically zero and is not read
   int norm_row_lo, norm_row_hi;  // rows [lo, hi) entering the residual sum (a slab sums only the rows it owns)
   int rows_per_tile;       // R (even)
@@ -252,14 +253,48 @@ __device__ __forceinline__ T residual_sel(const StencilScalars<T>& s, T uc, T up
   return residual_fast<T>(s, uc, up, dn, rt, lf, f);
 }
 
+// Variable-coefficient operator  A u = -div(a grad u) + shift*u, arithmetic-mean face coefficients of the nodal field a
+// (mg_varcoef.cu states the discretisation; no reference operator exists).  The strict kernel's operation
+// order is kept -- two rounded products and their rounded sum per direction, a TRUE division by the per-point diagonal --
+// with two exact rewrites: the halving of the face means is folded into the scaling (s = a_nb + a_c is twice the face
+// coefficient; multiplying by 0.5 commutes with every rounding), and the divisions by hx^2, hy^2 become multiplications
+// by hcx = 0.5/hx^2, hcy = 0.5/hy^2, exact when the spacings are powers of two.  On such grids the fused passes are
+// therefore bit-identical to mg_varcoef_smooth_rbgs / mg_varcoef_residual; otherwise they differ by a few ulp.
+template <bool NOBLEND, typename T>
+__device__ __forceinline__ T relax_var(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T rhs, T ac, T a_up, T a_dn,
+                                       T a_rt, T a_lf) {
+  using A = Strict<T>;
+  const T se = A::add(a_up, ac), sw = A::add(a_dn, ac), sn = A::add(a_rt, ac), ss = A::add(a_lf, ac);
+  const T x = A::add(A::mul(se, up), A::mul(sw, dn));
+  const T y = A::add(A::mul(sn, rt), A::mul(ss, lf));
+  const T nb = A::add(A::mul(x, s.ihx2), A::mul(y, s.ihy2));  // VARCOEF scalars: ihx2 = 0.5/hx^2, ihy2 = 0.5/hy^2
+  const T diag = A::add(A::add(A::mul(A::add(se, sw), s.ihx2), A::mul(A::add(sn, ss), s.ihy2)), s.shift);
+  const T unew = A::div(A::add(rhs, nb), diag);
+  if (NOBLEND) return unew;  // omega == 1
+  return A::add(A::mul(s.one_minus_omega, uc), A::mul(s.omega, unew));
+}
+template <typename T>
+__device__ __forceinline__ T residual_var(const StencilScalars<T>& s, T uc, T up, T dn, T rt, T lf, T f, T ac, T a_up, T a_dn,
+                                          T a_rt, T a_lf) {
+  using A = Strict<T>;
+  const T se = A::add(a_up, ac), sw = A::add(a_dn, ac), sn = A::add(a_rt, ac), ss = A::add(a_lf, ac);
+  const T x = A::mul(A::add(A::mul(se, A::sub(uc, up)), A::mul(sw, A::sub(uc, dn))), s.ihx2);
+  const T y = A::mul(A::add(A::mul(sn, A::sub(uc, rt)), A::mul(ss, A::sub(uc, lf))), s.ihy2);
+  return A::sub(f, A::add(A::add(x, y), A::mul(s.shift, uc)));
+}
+
 // ---------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------
-template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH, int WARPS, int NSTAGE, int RB>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH, int WARPS, int NSTAGE, int RB,
+          bool VARCOEF = false>
 __global__ void __launch_bounds__(WARPS * 32)
     rbgs_stream_kernel(const __grid_constant__ CUtensorMap map_u, const __grid_constant__ CUtensorMap map_f,
-                       const __grid_constant__ CUtensorMap map_e, const PassParams p, const StencilScalars<T> sc) {
+                       const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_a,
+                       const PassParams p, const StencilScalars<T> sc) {
   constexpr int NS = num_stages(SMOOTH, NU);  // pipeline stages; the row loaded NS steps ago is final
+  static_assert(!VARCOEF || (SMOOTH == SMOOTH_RBGS && LOADER == LOADER_TMA),
+                "variable coefficients: red-black GS, TMA-staged only");
   using G = Geometry<NS, BACK>;
   static_assert(RB % 2 == 0, "row parity must be static inside a box");
   static_assert(FRONT != FRONT_ADDFINE || sizeof(T) == 8, "ADDFINE adds an fp32 correction to an fp64 iterate");
@@ -276,7 +311,9 @@ __global__ void __launch_bounds__(WARPS * 32)
   constexpr int CALIGN = 16 / (int)sizeof(T) - 1;  // box start rounded down to 16 bytes
   constexpr uint32_t CBOX_TX = STAGE_COARSE ? (RB / 2 + 1) * COARSE_BOX_W * sizeof(T) : 0;  // bytes TMA delivers
   constexpr uint32_t CBOX_BYTES = (CBOX_TX + 127u) & ~127u;                                     // ring slot (128-B aligned)
-  constexpr uint32_t STAGE_BYTES = 2 * BOX_BYTES + EBOX_BYTES + CBOX_BYTES;
+  constexpr uint32_t ABOX_BYTES = VARCOEF ? BOX_BYTES : 0;  // nodal coefficient rows ride the same ring (+1 word / point)
+  constexpr uint32_t ABOX_OFF = 2 * BOX_BYTES + EBOX_BYTES + CBOX_BYTES;
+  constexpr uint32_t STAGE_BYTES = ABOX_OFF + ABOX_BYTES;
 
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t full_bar[WARPS][NSTAGE];
@@ -335,8 +372,9 @@ __global__ void __launch_bounds__(WARPS * 32)
     const int row0 = i_begin + box * RB;
     if (LOADER == LOADER_TMA) {
       if (lane == 0) {
-        mbar_expect_tx(&full_bar[warp][stage], (u_zero ? 0u : BOX_BYTES) + BOX_BYTES + EBOX_BYTES + CBOX_TX);
+        mbar_expect_tx(&full_bar[warp][stage], (u_zero ? 0u : BOX_BYTES) + BOX_BYTES + EBOX_BYTES + CBOX_TX + ABOX_BYTES);
         if (!u_zero) tma_load_2d(dst_u, &map_u, g0, row0, &full_bar[warp][stage]);
+        if (VARCOEF) tma_load_2d(dst_u + ABOX_OFF, &map_a, g0, row0, &full_bar[warp][stage]);
         tma_load_2d(dst_f, &map_f, g0, row0, &full_bar[warp][stage]);
         if (FRONT == FRONT_ADDFINE) tma_load_2d(dst_e, &map_e, g0, row0, &full_bar[warp][stage]);
         // coarse rows row0/2 .. row0/2 + RB/2, coarse columns g0/2 .. (out-of-range parts arrive as zeros)
@@ -403,6 +441,13 @@ __global__ void __launch_bounds__(WARPS * 32)
   for (int a = 0; a <= NS; ++a)
 #pragma unroll
     for (int e = 0; e < 4; ++e) pj[a][e] = (T)0;
+  // variable coefficients: the same row window for the nodal field a; [4] / [5] = the left / right neighbour column of
+  // the lane's elements 0 / 3 (one shuffle each when the row arrives: a does not change between the stages)
+  T ac[VARCOEF ? WR : 1][6];
+#pragma unroll
+  for (int a = 0; a < (VARCOEF ? WR : 1); ++a)
+#pragma unroll
+    for (int e = 0; e < 6; ++e) ac[a][e] = (T)0;
   T rr[3][4];  // residual rows (BACK_RESTRICT): rr[0] newest
 #pragma unroll
   for (int a = 0; a < 3; ++a)
@@ -452,7 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32)
   // su / sf / se: shared-window addresses of this lane's 4 elements of the box's first u / f / fp32-correction row;
   // sc_box: of the box's coarse slab (STAGE_COARSE)
   auto process_box = [&](auto masked_tag, const int ib, const uint32_t su, const uint32_t sf, const uint32_t se,
-                         const uint32_t sc_box) {
+                         const uint32_t sc_box, const uint32_t sa) {
     constexpr bool MASKED = decltype(masked_tag)::value;
     if (STAGE_COARSE) {
       read_coarse_row(sc_box, 0, c0);
@@ -475,6 +520,12 @@ __global__ void __launch_bounds__(WARPS * 32)
       for (int a = FR - 1; a > 0; --a)
 #pragma unroll
         for (int e = 0; e < 4; ++e) fr[a][e] = fr[a - 1][e];
+      if (VARCOEF) {
+#pragma unroll
+        for (int a = WR - 1; a > 0; --a)
+#pragma unroll
+          for (int e = 0; e < 6; ++e) ac[a][e] = ac[a - 1][e];
+      }
 
       // (1) newest row from the ring
       if (u_zero) {
@@ -484,6 +535,13 @@ __global__ void __launch_bounds__(WARPS * 32)
         lds4(su + (uint32_t)(k * STRIP * (int)sizeof(T)), w[0]);
       }
       lds4(sf + (uint32_t)(k * STRIP * (int)sizeof(T)), fr[0]);
+      if (VARCOEF) {
+        T a4[4];
+        lds4(sa + (uint32_t)(k * STRIP * (int)sizeof(T)), a4);
+        ac[0][0] = a4[0]; ac[0][1] = a4[1]; ac[0][2] = a4[2]; ac[0][3] = a4[3];
+        ac[0][4] = shfl_up1(a4[3]);
+        ac[0][5] = shfl_dn1(a4[0]);
+      }
 
       // (1a) FRONT_ADDFINE: u += (T)e  (rows/columns outside the domain hold zeros in both arrays)
       if (FRONT == FRONT_ADDFINE) {
@@ -551,14 +609,32 @@ __global__ void __launch_bounds__(WARPS * 32)
           const int e0 = (kpar + s + ((s - 1) & 1)) & 1;  // first updated element, compile-time after unrolling
           if (e0 == 0) {
             const T lfx = shfl_up1(w[s][3]);
-            const T n0 = relax_sel<SIMPLE, T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
-            const T n2 = relax_sel<SIMPLE, T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
+            T n0, n2;
+            if (VARCOEF) {
+              constexpr int sa_ = VARCOEF ? 1 : 0;  // keeps the indices inside ac[1][6] in the constant-coefficient kernels
+              n0 = relax_var<SIMPLE, T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0], ac[s * sa_][0],
+                                        ac[(s - 1) * sa_][0], ac[(s + 1) * sa_][0], ac[s * sa_][1], ac[s * sa_][4]);
+              n2 = relax_var<SIMPLE, T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2], ac[s * sa_][2],
+                                        ac[(s - 1) * sa_][2], ac[(s + 1) * sa_][2], ac[s * sa_][3], ac[s * sa_][1]);
+            } else {
+              n0 = relax_sel<SIMPLE, T>(sc, w[s][0], w[s - 1][0], w[s + 1][0], w[s][1], lfx, fr[s][0]);
+              n2 = relax_sel<SIMPLE, T>(sc, w[s][2], w[s - 1][2], w[s + 1][2], w[s][3], w[s][1], fr[s][2]);
+            }
             w[s][0] = (!MASKED || (upd & 1u)) ? n0 : w[s][0];
             w[s][2] = (!MASKED || (upd & 4u)) ? n2 : w[s][2];
           } else {
             const T rtx = shfl_dn1(w[s][0]);
-            const T n1 = relax_sel<SIMPLE, T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
-            const T n3 = relax_sel<SIMPLE, T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
+            T n1, n3;
+            if (VARCOEF) {
+              constexpr int sa_ = VARCOEF ? 1 : 0;
+              n1 = relax_var<SIMPLE, T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1], ac[s * sa_][1],
+                                        ac[(s - 1) * sa_][1], ac[(s + 1) * sa_][1], ac[s * sa_][2], ac[s * sa_][0]);
+              n3 = relax_var<SIMPLE, T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3], ac[s * sa_][3],
+                                        ac[(s - 1) * sa_][3], ac[(s + 1) * sa_][3], ac[s * sa_][5], ac[s * sa_][2]);
+            } else {
+              n1 = relax_sel<SIMPLE, T>(sc, w[s][1], w[s - 1][1], w[s + 1][1], w[s][2], w[s][0], fr[s][1]);
+              n3 = relax_sel<SIMPLE, T>(sc, w[s][3], w[s - 1][3], w[s + 1][3], rtx, w[s][2], fr[s][3]);
+            }
             w[s][1] = (!MASKED || (upd & 2u)) ? n1 : w[s][1];
             w[s][3] = (!MASKED || (upd & 8u)) ? n3 : w[s][3];
           }
@@ -595,10 +671,23 @@ __global__ void __launch_bounds__(WARPS * 32)
           if (!MASKED || (q2 >= 1 && q2 <= nx - 2)) {
             const T lfx = shfl_up1(w[A][3]);
             const T rtx = shfl_dn1(w[A][0]);
-            const T r0 = residual_sel<SIMPLE, T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
-            const T r1 = residual_sel<SIMPLE, T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
-            const T r2 = residual_sel<SIMPLE, T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
-            const T r3 = residual_sel<SIMPLE, T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
+            T r0, r1, r2, r3;
+            if (VARCOEF) {
+              constexpr int B0 = VARCOEF ? A : 0, Bm = VARCOEF ? A - 1 : 0, Bp = VARCOEF ? A + 1 : 0;
+              r0 = residual_var<T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0], ac[B0][0], ac[Bm][0], ac[Bp][0],
+                                   ac[B0][1], ac[B0][4]);
+              r1 = residual_var<T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1], ac[B0][1], ac[Bm][1],
+                                   ac[Bp][1], ac[B0][2], ac[B0][0]);
+              r2 = residual_var<T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2], ac[B0][2], ac[Bm][2],
+                                   ac[Bp][2], ac[B0][3], ac[B0][1]);
+              r3 = residual_var<T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3], ac[B0][3], ac[Bm][3], ac[Bp][3],
+                                   ac[B0][5], ac[B0][2]);
+            } else {
+              r0 = residual_sel<SIMPLE, T>(sc, w[A][0], w[A - 1][0], w[A + 1][0], w[A][1], lfx, fr[A][0]);
+              r1 = residual_sel<SIMPLE, T>(sc, w[A][1], w[A - 1][1], w[A + 1][1], w[A][2], w[A][0], fr[A][1]);
+              r2 = residual_sel<SIMPLE, T>(sc, w[A][2], w[A - 1][2], w[A + 1][2], w[A][3], w[A][1], fr[A][2]);
+              r3 = residual_sel<SIMPLE, T>(sc, w[A][3], w[A - 1][3], w[A + 1][3], rtx, w[A][2], fr[A][3]);
+            }
             r[0] = (!MASKED || (upd & 1u)) ? r0 : fr[A][0];
             r[1] = (!MASKED || (upd & 2u)) ? r1 : fr[A][1];
             r[2] = (!MASKED || (upd & 4u)) ? r2 : fr[A][2];
@@ -688,14 +777,15 @@ __global__ void __launch_bounds__(WARPS * 32)
     const uint32_t sf = su + BOX_BYTES;
     const uint32_t sc_box = sbox + 2 * BOX_BYTES;              // coarse slab (STAGE_COARSE) ...
     const uint32_t se = sc_box + (uint32_t)(lane * LANE_V * 4);  // ... or fp32 correction rows (FRONT_ADDFINE)
+    const uint32_t sa = su + ABOX_OFF;                           // nodal coefficient rows (VARCOEF)
     const int ib = i_begin + box * RB;
     // interior fast path: every row evaluated in this box (oldest: ib - NS - 1 with a BACK stage) and the
     // newest row ib + RB - 1 are interior rows, and the strip has no boundary column
     // (with restriction also the centre row q2 - 1 of the oldest coarse row, hence 3 instead of 1)
     constexpr int OLDEST = NS + (BACK == BACK_RESTRICT ? 3 : (HAS_BACK ? 1 : 0));
     const bool fast = strip_interior && (ib - OLDEST >= 1) && (ib + RB - 1 <= nx - 2);
-    if (fast) process_box(FalseTag{}, ib, su, sf, se, sc_box);
-    else process_box(TrueTag{}, ib, su, sf, se, sc_box);
+    if (fast) process_box(FalseTag{}, ib, su, sf, se, sc_box, sa);
+    else process_box(TrueTag{}, ib, su, sf, se, sc_box, sa);
 
     // refill this stage with box + NSTAGE
     __syncwarp();

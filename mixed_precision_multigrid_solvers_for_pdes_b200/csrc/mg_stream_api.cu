@@ -9,6 +9,8 @@ int launch_pass_f32_tma(int, int, int, bool, int, const Maps&, const PassParams&
 int launch_pass_f32_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
 int launch_pass_f64_tma(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
 int launch_pass_f64_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f32_var(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_var(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -77,7 +79,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
                     int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_ci, int64_t ld_co, int64_t ld_fi,
                     int64_t ld_ro, double hx, double hy, double omega, double coefficient, int sweeps, int dtype,
                     int front, int back, int flags, void* stream, const char* what, int norm_lo = 0,
-                    int norm_hi = -1, double shift = 0.0) {
+                    int norm_hi = -1, double shift = 0.0, const void* a = nullptr, int64_t ld_a = 0) {
+  const bool varcoef = a != nullptr;  // -div(a grad u) + shift*u with the nodal coefficient field a
   const bool cpa = (flags & MG_VC_LOADER_CPASYNC) != 0;
   const bool store = (flags & MG_VC_NO_STORE) == 0;
   const bool u_zero = (flags & MG_VC_U_ZERO) != 0;
@@ -88,6 +91,11 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   if (!f || nx < 3 || ny < 3 || ld_f < ny || hx <= 0 || hy <= 0 || !(shift >= 0.0)) return MG_ERR_BADARG;
   if (!u_zero && (!u_in || ld_in < ny)) return MG_ERR_BADARG;
   if (sweeps < 0 || sweeps > 2) return MG_ERR_UNSUPPORTED;
+  if (varcoef) {
+    // red-black GS, TMA-staged; fp64 passes carry one sweep (register budget of the three row windows)
+    if (cpa || smooth != SMOOTH_RBGS || (dtype == MG_F64 && sweeps > 1) || ld_a < ny) return MG_ERR_UNSUPPORTED;
+    if (front == FRONT_PROLONG && back == BACK_RESTRICT) return MG_ERR_UNSUPPORTED;
+  }
   if (smooth == SMOOTH_JACOBI && cpa && sweeps > 0) return MG_ERR_UNSUPPORTED;  // Jacobi passes are TMA-staged only
   if (store && (!u_out || ld_out < ny || u_out == u_in)) return MG_ERR_BADARG;
   if (!store && back == BACK_NONE) return MG_ERR_BADARG;
@@ -113,7 +121,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   if ((!u_zero && misaligned(u_in, ld_in, esz)) || misaligned(f, ld_f, esz) || (store && misaligned(u_out, ld_out, esz)) ||
       (front == FRONT_PROLONG && misaligned(coarse_in, ld_ci, esz)) ||
       (back == BACK_RESTRICT && misaligned(coarse_out, ld_co, esz)) ||
-      (front == FRONT_ADDFINE && misaligned(fine_in, ld_fi, 4)) || (back == BACK_RESID && misaligned(resid_out, ld_ro, 4)))
+      (front == FRONT_ADDFINE && misaligned(fine_in, ld_fi, 4)) || (back == BACK_RESID && misaligned(resid_out, ld_ro, 4)) ||
+      (varcoef && misaligned(a, ld_a, esz)))
     return MG_ERR_ALIGN;
 
   PassParams p;
@@ -121,6 +130,7 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   p.u_in = u_zero ? f : u_in;  // never dereferenced when u_zero
   p.u_out = u_out; p.f = f; p.coarse_in = coarse_in; p.coarse_out = coarse_out;
   p.fine_in = fine_in; p.resid_out = resid_out;
+  p.a = a; p.ld_a = ld_a;
   p.partials = workspace;
   p.nx = nx; p.ny = ny; p.nxc = nxc; p.nyc = nyc;
   p.ld_in = u_zero ? ld_f : ld_in; p.ld_out = ld_out; p.ld_f = ld_f; p.ld_ci = ld_ci; p.ld_co = ld_co;
@@ -141,6 +151,7 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
     if (rc == MG_OK && front == FRONT_ADDFINE) rc = make_map(&m.e, fine_in, nx, ny, ld_fi, MG_F32);
     if (rc == MG_OK && front == FRONT_PROLONG)  // the coarse correction rides the TMA ring (see StageCoarse)
       rc = make_map(&m.e, coarse_in, nxc, nyc, ld_ci, dtype, COARSE_BOX_W, RB / 2 + 1);
+    if (rc == MG_OK && varcoef) rc = make_map(&m.a, a, nx, ny, ld_a, dtype);
     if (rc != MG_OK) return rc;
   }
   cudaStream_t st = as_stream(stream);
@@ -148,7 +159,19 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   // a shift; both pin every rounding, so results never depend on the tiling or the slab decomposition)
   const bool simple = (omega == 1.0) && (hx == hy);
   int rc;
-  if (dtype == MG_F64) {
+  if (varcoef) {
+    // the variable-coefficient point update scales by 0.5/h^2 (the halving of the face means folded in) and takes
+    // `shift` as is; `noblend` = (omega == 1)
+    if (dtype == MG_F64) {
+      auto sc = make_scalars<double>(hx, hy, omega, coefficient, shift);
+      sc.ihx2 = 0.5 / sc.hx2; sc.ihy2 = 0.5 / sc.hy2;
+      rc = launch_pass_f64_var(sweeps, front, back, omega == 1.0, m, p, sc, st);
+    } else {
+      auto sc = make_scalars<float>(hx, hy, omega, coefficient, shift);
+      sc.ihx2 = 0.5f / sc.hx2; sc.ihy2 = 0.5f / sc.hy2;
+      rc = launch_pass_f32_var(sweeps, front, back, omega == 1.0, m, p, sc, st);
+    }
+  } else if (dtype == MG_F64) {
     auto sc = make_scalars<double>(hx, hy, omega, coefficient, shift);
     rc = cpa ? launch_pass_f64_cpa(sweeps, front, back, simple, smooth, m, p, sc, st)
              : launch_pass_f64_tma(sweeps, front, back, simple, smooth, m, p, sc, st);
@@ -223,6 +246,35 @@ int mg_vc_defect_pass(const void* u_in, void* u_out, const void* f, const void* 
   return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
                   workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, coefficient, 0, MG_F64, front,
                   back, fl, stream, "mg_vc_defect_pass");
+}
+
+int mg_vcv_pass_slab(const void* u_in, void* u_out, const void* f, const void* a, const void* coarse_in, void* coarse_out,
+                     double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out, int64_t ld_f,
+                     int64_t ld_a, int64_t ld_ci, int64_t ld_co, double hx, double hy, double omega, int sweeps, int dtype,
+                     int flags, int norm_row_lo, int norm_row_hi, double shift, void* stream) {
+  if (!a) return MG_ERR_BADARG;
+  if ((flags & MG_VC_RESTRICT) && (flags & MG_VC_NORM)) return MG_ERR_UNSUPPORTED;
+  if (flags & (MG_VC_JACOBI | MG_VC_LOADER_CPASYNC)) return MG_ERR_UNSUPPORTED;
+  const int front = (flags & MG_VC_PROLONG) ? FRONT_PROLONG : FRONT_NONE;
+  const int back = (flags & MG_VC_RESTRICT) ? BACK_RESTRICT : ((flags & MG_VC_NORM) ? BACK_NORM : BACK_NONE);
+  return run_pass(u_in, u_out, f, coarse_in, coarse_out, nullptr, nullptr, sumsq_out, workspace, nx, ny, ld_in, ld_out,
+                  ld_f, ld_ci, ld_co, 0, 0, hx, hy, omega, 1.0, sweeps, dtype, front, back, flags, stream,
+                  "mg_vcv_pass_slab", norm_row_lo, norm_row_hi, shift, a, ld_a);
+}
+
+int mg_vcv_defect_pass_slab(const void* u_in, void* u_out, const void* f, const void* a, const void* e_in, void* r_out,
+                            double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in, int64_t ld_out,
+                            int64_t ld_f, int64_t ld_a, int64_t ld_e, int64_t ld_r, double hx, double hy, int flags,
+                            int norm_row_lo, int norm_row_hi, double shift, void* stream) {
+  if (!a) return MG_ERR_BADARG;
+  if (flags & (MG_VC_JACOBI | MG_VC_LOADER_CPASYNC)) return MG_ERR_UNSUPPORTED;
+  const int front = e_in ? FRONT_ADDFINE : FRONT_NONE;
+  const int back = r_out ? BACK_RESID : BACK_NONE;
+  int fl = flags & ~(MG_VC_PROLONG | MG_VC_RESTRICT | MG_VC_NORM);
+  if (!e_in) fl |= MG_VC_NO_STORE;
+  return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
+                  workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, 1.0, 0, MG_F64, front, back, fl,
+                  stream, "mg_vcv_defect_pass_slab", norm_row_lo, norm_row_hi, shift, a, ld_a);
 }
 
 int mg_vc_smooth(const void* u_in, void* u_out, const void* f, int nx, int ny, int64_t ld_in, int64_t ld_out,

@@ -14,17 +14,18 @@ template <typename T> struct Stages { static constexpr int N = 3; };
 template <> struct Stages<double> { static constexpr int N = 2; };
 
 struct Maps {
-  CUtensorMap u, f, e;
+  CUtensorMap u, f, e, a;
 };
 
-template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH = SMOOTH_RBGS>
+template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH = SMOOTH_RBGS, bool VARCOEF = false>
 static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
   // fp32 prolongation passes carry the coarse slab in every stage: 2 stages keep 5 blocks (20 warps) per SM
-  constexpr int NS = (sizeof(T) == 4 && FRONT == FRONT_PROLONG && LOADER == LOADER_TMA) ? 2 : Stages<T>::N;
-  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, SMOOTH, WARPS, NS, RB>;
+  constexpr int NS = ((sizeof(T) == 4 && FRONT == FRONT_PROLONG && LOADER == LOADER_TMA) || VARCOEF) ? 2 : Stages<T>::N;
+  auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, SMOOTH, WARPS, NS, RB, VARCOEF>;
   constexpr bool stage_coarse = StageCoarse<T, FRONT, BACK, LOADER>::value;
   constexpr size_t cbox = stage_coarse ? ((((size_t)(RB / 2 + 1) * COARSE_BOX_W * sizeof(T)) + 127) & ~(size_t)127) : 0;
-  constexpr size_t stage_bytes = 2 * (size_t)RB * STRIP * sizeof(T) + (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0) + cbox;
+  constexpr size_t stage_bytes = (VARCOEF ? 3 : 2) * (size_t)RB * STRIP * sizeof(T) +
+                                 (FRONT == FRONT_ADDFINE ? (size_t)RB * STRIP * 4 : 0) + cbox;
   constexpr size_t smem = (size_t)WARPS * NS * stage_bytes;
   static bool configured[64] = {false};
   int dev = 0;
@@ -35,7 +36,7 @@ static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T
   }
   const int ntiles = (p.nx + p.rows_per_tile - 1) / p.rows_per_tile;
   dim3 grid((p.nstrips + WARPS - 1) / WARPS, ntiles);
-  kern<<<grid, WARPS * 32, smem, st>>>(m.u, m.f, m.e, p, sc);
+  kern<<<grid, WARPS * 32, smem, st>>>(m.u, m.f, m.e, m.a, p, sc);
   return 0;
 }
 
@@ -70,6 +71,29 @@ int launch_pass(int nu, int front, int back, bool simple, int smooth, const Maps
     MG_CASE(0, FRONT_NONE, BACK_RESID) MG_CASE(0, FRONT_ADDFINE, BACK_RESID) MG_CASE(0, FRONT_ADDFINE, BACK_NONE)
   }
 #undef MG_CASE
+  return MG_ERR_UNSUPPORTED;
+}
+
+// Variable-coefficient passes (-div(a grad u) + shift*u): red-black GS, TMA-staged; `noblend` = (omega == 1).
+// fp64 keeps to one sweep per pass: a 2-sweep fp64 pass would hold 188 registers of row windows (u, f and the
+// coefficient rows with their shuffled neighbour columns) before any temporaries.
+template <typename T>
+int launch_pass_var(int nu, int front, int back, bool noblend, const Maps& m, const PassParams& p,
+                    const StencilScalars<T>& sc, cudaStream_t st) {
+#define MG_VCASE(NU_, FR_, BK_)                                                                              \
+  if (nu == NU_ && front == FR_ && back == BK_)                                                              \
+    return noblend ? launch_one<T, NU_, FR_, BK_, LOADER_TMA, true, SMOOTH_RBGS, true>(m, p, sc, st)          \
+                   : launch_one<T, NU_, FR_, BK_, LOADER_TMA, false, SMOOTH_RBGS, true>(m, p, sc, st);
+  MG_VCASE(0, FRONT_NONE, BACK_RESTRICT) MG_VCASE(0, FRONT_NONE, BACK_NORM) MG_VCASE(0, FRONT_PROLONG, BACK_NONE)
+  MG_VCASE(1, FRONT_NONE, BACK_NONE) MG_VCASE(1, FRONT_NONE, BACK_RESTRICT) MG_VCASE(1, FRONT_NONE, BACK_NORM)
+  MG_VCASE(1, FRONT_PROLONG, BACK_NONE) MG_VCASE(1, FRONT_PROLONG, BACK_NORM)
+  if constexpr (sizeof(T) == 4) {
+    MG_VCASE(2, FRONT_NONE, BACK_NONE) MG_VCASE(2, FRONT_NONE, BACK_RESTRICT) MG_VCASE(2, FRONT_NONE, BACK_NORM)
+    MG_VCASE(2, FRONT_PROLONG, BACK_NONE) MG_VCASE(2, FRONT_PROLONG, BACK_NORM)
+  } else {  // mixed-precision defect-correction passes (fp64 iterate, fp32 correction / residual)
+    MG_VCASE(0, FRONT_NONE, BACK_RESID) MG_VCASE(0, FRONT_ADDFINE, BACK_RESID) MG_VCASE(0, FRONT_ADDFINE, BACK_NONE)
+  }
+#undef MG_VCASE
   return MG_ERR_UNSUPPORTED;
 }
 

@@ -63,6 +63,62 @@ __global__ void __launch_bounds__(VBX* VBY) varcoef_rbgs_kernel(T* __restrict__ 
   p[0] = A::add(A::mul(s.one_minus_omega, p[0]), A::mul(s.omega, unew));
 }
 
+// Coarsest level: <= maxit x [one red-black GS sweep, residual, h-scaled L2 norm over all points], stop below tol --
+// IterativeSolver.solve (solvers/base.py:258-285) with VariableCoefficientSmoother as the solver, in ONE launch of one
+// block with the stopping test in the kernel (the host-driven loop costs a stream synchronisation per sweep).
+// Same strict arithmetic as the two kernels above.
+constexpr int VCS_THREADS = 256;
+template <typename T>
+__global__ void __launch_bounds__(VCS_THREADS) varcoef_coarse_solve_kernel(T* __restrict__ u, const T* __restrict__ f,
+                                                                          const T* __restrict__ a, int nx, int ny,
+                                                                          int64_t ldu, int64_t ldf, int64_t lda,
+                                                                          VarScalars<T> s, double hxhy, double tol, int maxit,
+                                                                          double* __restrict__ info) {
+  using A = Strict<T>;
+  __shared__ double red[32];
+  const int n = nx * ny;
+  int it = 1;
+  double norm = 0.0;
+  for (; it <= maxit; ++it) {
+    for (int colour = 0; colour < 2; ++colour) {
+      for (int k = threadIdx.x; k < n; k += VCS_THREADS) {
+        const int i = k / ny, j = k - i * ny;
+        if (i < 1 || i > nx - 2 || j < 1 || j > ny - 2 || ((i + j) & 1) != colour) continue;
+        T* p = u + (int64_t)i * ldu + j;
+        T ae, aw, an, as;
+        faces<T>(a + (int64_t)i * lda + j, lda, ae, aw, an, as);
+        const T nb = A::add(A::div(A::add(A::mul(ae, p[ldu]), A::mul(aw, p[-ldu])), s.hx2),
+                            A::div(A::add(A::mul(an, p[1]), A::mul(as, p[-1])), s.hy2));
+        const T diag = A::add(A::add(A::div(A::add(ae, aw), s.hx2), A::div(A::add(an, as), s.hy2)), s.shift);
+        const T unew = A::div(A::add(f[(int64_t)i * ldf + j], nb), diag);
+        p[0] = A::add(A::mul(s.one_minus_omega, p[0]), A::mul(s.omega, unew));
+      }
+      __syncthreads();
+    }
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < n; k += VCS_THREADS) {
+      const int i = k / ny, j = k - i * ny;
+      T v = f[(int64_t)i * ldf + j];
+      if (i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+        const T* p = u + (int64_t)i * ldu + j;
+        T ae, aw, an, as;
+        faces<T>(a + (int64_t)i * lda + j, lda, ae, aw, an, as);
+        const T x = A::div(A::add(A::mul(ae, A::sub(p[0], p[ldu])), A::mul(aw, A::sub(p[0], p[-ldu]))), s.hx2);
+        const T y = A::div(A::add(A::mul(an, A::sub(p[0], p[1])), A::mul(as, A::sub(p[0], p[-1]))), s.hy2);
+        v = A::sub(v, A::add(A::add(x, y), A::mul(s.shift, p[0])));
+      }
+      acc += (double)A::mul(v, v);
+    }
+    acc = block_reduce(acc, red);
+    norm = sqrt(hxhy * acc);
+    if (norm < tol) break;
+  }
+  if (info != nullptr && threadIdx.x == 0) {
+    info[0] = (double)(it > maxit ? maxit : it);
+    info[1] = norm;
+  }
+}
+
 template <typename T>
 static VarScalars<T> var_scalars(double hx, double hy, double shift, double omega) {
   VarScalars<T> s;
@@ -120,6 +176,26 @@ int mg_varcoef_smooth_rbgs(void* u, const void* f, const void* a, int nx, int ny
                                                     colour, var_scalars<float>(hx, hy, shift, omega));
     }
   return check_launch("mg_varcoef_smooth_rbgs", 2 * sweeps);
+}
+
+int mg_varcoef_coarse_solve(void* u, const void* f, const void* a, int nx, int ny, int64_t ld_u, int64_t ld_f, int64_t ld_a,
+                            double hx, double hy, double shift, double omega, double tolerance, int max_iterations,
+                            double* info, int dtype, void* stream) {
+  if (!u || !f || !a || nx < 3 || ny < 3 || ld_u < ny || ld_f < ny || ld_a < ny || hx <= 0 || hy <= 0 || !(shift >= 0) ||
+      max_iterations < 1)
+    return MG_ERR_BADARG;
+  if (dtype != MG_F32 && dtype != MG_F64) return MG_ERR_DTYPE;
+  if ((int64_t)nx * ny > 65 * 65) return MG_ERR_UNSUPPORTED;  // one block: coarsest grids only
+  cudaStream_t st = as_stream(stream);
+  if (dtype == MG_F64)
+    varcoef_coarse_solve_kernel<double><<<1, VCS_THREADS, 0, st>>>((double*)u, (const double*)f, (const double*)a, nx, ny,
+                                                                   ld_u, ld_f, ld_a, var_scalars<double>(hx, hy, shift, omega),
+                                                                   hx * hy, tolerance, max_iterations, info);
+  else
+    varcoef_coarse_solve_kernel<float><<<1, VCS_THREADS, 0, st>>>((float*)u, (const float*)f, (const float*)a, nx, ny, ld_u,
+                                                                  ld_f, ld_a, var_scalars<float>(hx, hy, shift, omega),
+                                                                  hx * hy, tolerance, max_iterations, info);
+  return check_launch("mg_varcoef_coarse_solve");
 }
 
 }  // extern "C"

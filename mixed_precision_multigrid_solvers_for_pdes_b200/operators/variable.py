@@ -69,7 +69,7 @@ class VariableCoefficientOperator(BaseOperator):
 class VariableCoefficientSmoother(IterativeSolver):
     """Red-black Gauss-Seidel for ``VariableCoefficientOperator`` (pass it as the `smoother` AND, for the coarsest
     level, as the `coarse_solver` of MultigridSolver.setup)."""
-    kind = "custom"
+    kind = "rbgs_var"  # the cycle engine fuses it (mg_vcv_* passes) together with VariableCoefficientOperator
 
     def __init__(self, operator: VariableCoefficientOperator, max_iterations: int = 1000, tolerance: float = 1e-8,
                  relaxation_parameter: float = 1.0, verbose: bool = False):

@@ -278,10 +278,12 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
             coarse_in: Optional[torch.Tensor] = None, coarse_out: Optional[torch.Tensor] = None,
             sumsq_out: Optional[torch.Tensor] = None, loader: str = "tma", rows: int = 0,
             u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0,
-            smoother: str = "rbgs", workspace: Optional[torch.Tensor] = None) -> None:
+            smoother: str = "rbgs", workspace: Optional[torch.Tensor] = None, a: Optional[torch.Tensor] = None) -> None:
     """One fused pass: [u += P coarse_in] -> `sweeps` RB-GS (``smoother="jacobi"``: damped Jacobi) sweeps ->
     [coarse_out = R(f - A u)] or [sumsq_out[0] = sum (f - A u)^2]; out of place u_in -> u_out (u_out=None:
-    nothing stored).  ``u_zero``: treat u_in as identically zero without reading it."""
+    nothing stored).  ``u_zero``: treat u_in as identically zero without reading it.  ``a``: nodal coefficient field
+    of the level -> the variable-coefficient operator -div(a grad u) + shift*u (mg_vcv_pass_slab; RB-GS only, fp64 at
+    most one sweep per pass; `coefficient` is not used)."""
     nx, ny = f.shape
     flags = (rows & 0xFFF) << 8
     if smoother == "jacobi":
@@ -309,6 +311,32 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     nlo, nhi = norm_rows if norm_rows is not None else (0, -1)
+    if a is not None:
+        if a.shape != f.shape or a.dtype != f.dtype:
+            raise ValueError("vc_pass: the coefficient field must have the shape and dtype of the level")
+        _lib.call("mg_vcv_pass_slab", None if u_zero else u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None,
+                  f.data_ptr(), a.data_ptr(),
+                  coarse_in.data_ptr() if coarse_in is not None else None,
+                  coarse_out.data_ptr() if coarse_out is not None else None,
+                  sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
+                  nx, ny, 0 if u_zero else ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(a),
+                  ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
+                  hx, hy, omega, sweeps, code(f.dtype), flags, nlo, nhi, shift, stream_ptr())
+    else:
+        _vc_pass_const(u_in, u_out, f, hx, hy, omega, coefficient, coarse_in, coarse_out, sumsq_out, ws, sweeps, flags,
+                       nlo, nhi, shift, u_zero)
+    if timed:
+        ev1.record()
+        tag = (("var:" if a is not None else "") + ("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "")
+               + f"{'jac' if smoother == 'jacobi' else 'rbgs'}{sweeps}"
+               + ("+R" if coarse_out is not None else "") + ("+N" if sumsq_out is not None else "")
+               + f"/{'f64' if f.dtype == torch.float64 else 'f32'}/{nx}x{ny}")
+        TIMER.records.append((tag, ev0, ev1))
+
+
+def _vc_pass_const(u_in, u_out, f, hx, hy, omega, coefficient, coarse_in, coarse_out, sumsq_out, ws, sweeps, flags, nlo, nhi,
+                   shift, u_zero) -> None:
+    nx, ny = f.shape
     _lib.call("mg_vc_pass_slab", None if u_zero else u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None,
               f.data_ptr(),
               coarse_in.data_ptr() if coarse_in is not None else None,
@@ -317,12 +345,6 @@ def vc_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, 
               nx, ny, 0 if u_zero else ld(u_in), ld(u_out) if u_out is not None else 0, ld(f),
               ld(coarse_in) if coarse_in is not None else 0, ld(coarse_out) if coarse_out is not None else 0,
               hx, hy, omega, coefficient, sweeps, code(f.dtype), flags, nlo, nhi, shift, stream_ptr())
-    if timed:
-        ev1.record()
-        tag = (("Z+" if u_zero else "") + ("P+" if coarse_in is not None else "") + f"{'jac' if smoother == 'jacobi' else 'rbgs'}{sweeps}"
-               + ("+R" if coarse_out is not None else "") + ("+N" if sumsq_out is not None else "")
-               + f"/{'f64' if f.dtype == torch.float64 else 'f32'}/{nx}x{ny}")
-        TIMER.records.append((tag, ev0, ev1))
 
 
 def _loader_flag(loader: str) -> int:
@@ -337,7 +359,8 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
                    e_in: Optional[torch.Tensor] = None, r_out: Optional[torch.Tensor] = None,
                    sumsq_out: Optional[torch.Tensor] = None, coefficient: float = -1.0, loader: str = "tma",
                    rows: int = 0, norm_rows: Optional[Tuple[int, int]] = None, shift: float = 0.0,
-                   workspace: Optional[torch.Tensor] = None, u_zero: bool = False) -> None:
+                   workspace: Optional[torch.Tensor] = None, u_zero: bool = False,
+                   a: Optional[torch.Tensor] = None) -> None:
     """Mixed-precision defect-correction pass on the fp64 iterate (one HBM pass):
     u_out = u_in + e_in (fp32 correction; None: u unchanged, nothing stored), r_out = fp32(f - A u_out),
     sumsq_out[0] = sum of the squared fp64 residual."""
@@ -360,15 +383,38 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     nlo, nhi = norm_rows if norm_rows is not None else (0, -1)
-    _lib.call("mg_vc_defect_pass_slab", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
-              e_in.data_ptr() if e_in is not None else None, r_out.data_ptr() if r_out is not None else None,
-              sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
-              nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(e_in) if e_in is not None else 0,
-              ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, shift, stream_ptr())
+    if a is not None:  # variable coefficients: the fp64 nodal field of the level
+        if a.shape != u_in.shape or a.dtype != torch.float64:
+            raise ValueError("vc_defect_pass: the coefficient field is fp64 and has the shape of the iterate")
+        _lib.call("mg_vcv_defect_pass_slab", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+                  a.data_ptr(), e_in.data_ptr() if e_in is not None else None,
+                  r_out.data_ptr() if r_out is not None else None,
+                  sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
+                  nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(a),
+                  ld(e_in) if e_in is not None else 0, ld(r_out) if r_out is not None else 0, hx, hy, flags, nlo, nhi,
+                  shift, stream_ptr())
+    else:
+        _lib.call("mg_vc_defect_pass_slab", u_in.data_ptr(), u_out.data_ptr() if u_out is not None else None, f.data_ptr(),
+                  e_in.data_ptr() if e_in is not None else None, r_out.data_ptr() if r_out is not None else None,
+                  sumsq_out.data_ptr() if sumsq_out is not None else None, ws.data_ptr() if ws is not None else None,
+                  nx, ny, ld(u_in), ld(u_out) if u_out is not None else 0, ld(f), ld(e_in) if e_in is not None else 0,
+                  ld(r_out) if r_out is not None else 0, hx, hy, coefficient, flags, nlo, nhi, shift, stream_ptr())
     if timed:
         ev1.record()
-        TIMER.records.append((("Z+" if u_zero else "") + ("update+" if e_in is not None else "")
+        TIMER.records.append((("var:" if a is not None else "") + ("Z+" if u_zero else "") + ("update+" if e_in is not None else "")
                               + ("resid32+N" if r_out is not None else "") + f"/f64/{nx}x{ny}", ev0, ev1))
+
+
+def varcoef_coarse_solve_(u: torch.Tensor, f: torch.Tensor, a: torch.Tensor, hx: float, hy: float, shift: float = 0.0,
+                          omega: float = 1.0, tolerance: float = 1e-12, max_iterations: int = 1000,
+                          info: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Coarsest-level solve for -div(a grad u) + shift*u: red-black GS sweeps to `tolerance` in one launch."""
+    _check_same_shape(u, f, "varcoef_coarse_solve")
+    nx, ny = u.shape
+    _lib.call("mg_varcoef_coarse_solve", u.data_ptr(), f.data_ptr(), a.data_ptr(), nx, ny, ld(u), ld(f), ld(a), hx, hy,
+              shift, omega, tolerance, max_iterations, info.data_ptr() if info is not None else None, code(u.dtype),
+              stream_ptr())
+    return u
 
 
 SMALL_CYCLE_SMEM_LIMIT = 200 * 1024

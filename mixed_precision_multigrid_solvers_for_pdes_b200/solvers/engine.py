@@ -23,6 +23,7 @@ from ..device import empty_field, require_cuda, torch_dtype
 
 
 _NATIVE_OPERATORS = ("LaplacianOperator", "HelmholtzOperator")  # operators the kernels implement directly
+_VARCOEF_OPERATOR = "VariableCoefficientOperator"               # -div(a grad u) + shift*u: the mg_vcv_* passes
 
 
 class _Buffers:
@@ -92,9 +93,11 @@ class CycleEngine:
         sm = self.smoother
         kind = getattr(sm, "kind", "custom")
         shift = getattr(self.operators[lvl], "shift", 0.0)
-        if shift and kind != "rbgs":
+        if shift and kind not in ("rbgs", "rbgs_var"):
             raise ValueError("a shifted (Helmholtz) operator is smoothed with red-black Gauss-Seidel only")
-        if kind == "jacobi":
+        if kind == "rbgs_var":  # strict per-colour kernels of the variable-coefficient smoother, in place
+            sm._smooth_device_(g, b.u, b.f, sweeps)
+        elif kind == "jacobi":
             ops.smooth_jacobi_(b.u, b.f, g.hx, g.hy, sm.omega, sweeps, tmp=b.tmp)
         elif kind == "rbgs":
             ops.smooth_rbgs_(b.u, b.f, g.hx, g.hy, sm.omega, sweeps, shift=shift)
@@ -120,6 +123,9 @@ class CycleEngine:
         if getattr(cs, "kind", None) == "lexgs" and coeff is not None and type(op).__name__ in _NATIVE_OPERATORS:
             ops.coarse_solve_lexgs_(b.u, b.f, g.hx, g.hy, cs.omega, coeff, cs.tolerance, cs.max_iterations,
                                     info=self.coarse_info, shift=getattr(op, "shift", 0.0))
+        elif getattr(cs, "kind", None) == "rbgs_var" and type(op).__name__ == _VARCOEF_OPERATOR:
+            ops.varcoef_coarse_solve_(b.u, b.f, op.coefficients(g.nx, g.ny, b.u.dtype), g.hx, g.hy, op.shift, cs.omega,
+                                      cs.tolerance, cs.max_iterations, info=self.coarse_info)
         else:  # any other IterativeSolver: its own solve loop (host-checked convergence)
             sol, _ = cs.solve(g, op, b.f, b.u, precision_manager)
             b.u.copy_(sol)
@@ -134,7 +140,8 @@ class CycleEngine:
         kind = getattr(self.smoother, "kind", None)
         # Jacobi: TMA-staged instantiations only, and (like the strict kernel) no Helmholtz shift
         jac = kind == "jacobi" and self.loader == "tma" and not getattr(op, "shift", 0.0)
-        ok = ((kind == "rbgs" or jac) and type(op).__name__ in _NATIVE_OPERATORS
+        var = kind == "rbgs_var" and type(op).__name__ == _VARCOEF_OPERATOR and self.loader == "tma"
+        ok = (((kind == "rbgs" or jac) and type(op).__name__ in _NATIVE_OPERATORS or var)
               and getattr(self.restriction_ops[lvl], "method", None) == "full_weighting"
               and getattr(self.prolongation_ops[lvl], "method", None) == "bilinear"
               and torch_dtype(level_dtypes[lvl]) == torch_dtype(level_dtypes[lvl + 1]))
@@ -191,42 +198,49 @@ class CycleEngine:
         g = self.levels[lvl].grid
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
-        coeff, omega, ld = self.operators[lvl].coefficient, self.smoother.omega, self.loader
-        sk = self.smoother.kind  # "rbgs" or "jacobi": same passes, the sweeps differ
-        sh = getattr(self.operators[lvl], "shift", 0.0)
-        # down: pre-smooth (2 sweeps per HBM pass) with residual + restriction fused into the last pass
+        op = self.operators[lvl]
+        omega, ld = self.smoother.omega, self.loader
+        sh = getattr(op, "shift", 0.0)
+        kw = {"omega": omega, "loader": ld, "shift": sh}
+        ms = 2  # sweeps per HBM pass
+        if type(op).__name__ == _VARCOEF_OPERATOR:  # variable coefficients: the level's nodal field rides along
+            kw["a"] = op.coefficients(g.nx, g.ny, b.u.dtype)
+            if b.u.dtype == torch.float64:
+                ms = 1
+        else:
+            kw["coefficient"] = op.coefficient
+            kw["smoother"] = self.smoother.kind  # "rbgs" or "jacobi": same passes, the sweeps differ
+        # down: pre-smooth (`ms` sweeps per HBM pass) with residual + restriction fused into the last pass
         n = self.pre
         if u_zero and n == 0:
             ops.zero_(b.u)  # nothing will overwrite the iterate before it is read
             u_zero = False
-        while n > 2:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=2, omega=omega, loader=ld, u_zero=u_zero, shift=sh, smoother=sk)
+        while n > ms:
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=ms, u_zero=u_zero, **kw)
             b.u, b.tmp = b.tmp, b.u
-            n -= 2
+            n -= ms
             u_zero = False
         if n > 0:
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, omega=omega, coefficient=coeff, coarse_out=c.f, loader=ld,
-                        u_zero=u_zero, shift=sh, smoother=sk)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, coarse_out=c.f, u_zero=u_zero, **kw)
             b.u, b.tmp = b.tmp, b.u
         else:
-            ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coefficient=coeff, coarse_out=c.f, loader=ld, shift=sh)
+            ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coarse_out=c.f, **kw)
         # the coarse error equation starts from e = 0: the first coarse pass is told so instead of reading zeros
         for rep in range(self._reps(lvl)):
             self.cycle(level_dtypes, lvl + 1, precision_manager, u_zero=(rep == 0))
         # up: prolongation + correction fused into the first post-smoothing pass, norm into the last
         n = self.post
-        first = min(n, 2)
+        first = min(n, ms)
         last = (n - first) == 0
-        ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, omega=omega, coefficient=coeff, coarse_in=c.u,
-                    sumsq_out=sumsq_out if last else None, loader=ld, shift=sh, smoother=sk, workspace=self.workspace)
+        ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=first, coarse_in=c.u, sumsq_out=sumsq_out if last else None,
+                    workspace=self.workspace, **kw)
         b.u, b.tmp = b.tmp, b.u
         n -= first
         while n > 0:
-            k = min(n, 2)
+            k = min(n, ms)
             n -= k
-            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, omega=omega, coefficient=coeff,
-                        sumsq_out=sumsq_out if n == 0 else None, loader=ld, shift=sh, smoother=sk,
-                        workspace=self.workspace)
+            ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=k, sumsq_out=sumsq_out if n == 0 else None,
+                        workspace=self.workspace, **kw)
             b.u, b.tmp = b.tmp, b.u
 
     # -- the recursion ------------------------------------------------------------------------------

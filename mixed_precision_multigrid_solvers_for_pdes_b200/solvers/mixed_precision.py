@@ -60,7 +60,7 @@ class MixedPrecisionMultigrid:
                  gpu_memory_fraction: Optional[float] = None, min_precision: Optional[str] = None,
                  strict_reference_norm: bool = False, kernels: str = "auto", loader: str = "tma", device=None,
                  use_cuda_graphs: bool = True, shift: float = 0.0, fmg: bool = False, verbose: bool = False,
-                 stop_on_rounding_floor: bool = True):
+                 stop_on_rounding_floor: bool = True, coefficient=None):
         key = str(precision_strategy).lower()
         if key not in _STRATEGIES:
             raise ValueError(f"Unknown precision strategy: {precision_strategy}")
@@ -101,6 +101,10 @@ class MixedPrecisionMultigrid:
         if shift < 0:
             raise ValueError("shift must be >= 0")
         self.shift = float(shift)
+        # Variable diffusion coefficient: solve -div(a grad u) + shift*u = f (README.md:175 advertises the problem class;
+        # the reference ships no operator).  `coefficient`: callable a(X, Y) evaluated on the fine grid,
+        # or an (nx, ny) array of nodal values (NumPy / CUDA tensor), a > 0.  None = the Poisson / Helmholtz operator.
+        self.coefficient = coefficient
         self.enable_precision_monitoring = False
         self.precision_switches: List[Dict[str, Any]] = []
         self._engine: Optional[CycleEngine] = None
@@ -140,12 +144,26 @@ class MixedPrecisionMultigrid:
             if c.nx < 5 or c.ny < 5:
                 break
             grids.append(c)
-        # coefficient -1: the convergent sign convention
-        op = HelmholtzOperator(-1.0, self.shift) if self.shift else LaplacianOperator(-1.0)
         L = len(grids)
+        if self.coefficient is not None:
+            from ..operators.variable import VariableCoefficientOperator, VariableCoefficientSmoother
+            if self.smoother_name.lower() not in ("red_black_gauss_seidel", "rbgs", "red_black", "gauss_seidel_rb"):
+                raise ValueError("variable coefficients are smoothed with red-black Gauss-Seidel")
+            a = self.coefficient(g.X, g.Y) if callable(self.coefficient) else self.coefficient
+            if not isinstance(a, torch.Tensor):
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (nx, ny)))
+            op = VariableCoefficientOperator(a, self.shift)
+            smoother = VariableCoefficientSmoother(op, relaxation_parameter=self.damping_factor)
+            coarse = VariableCoefficientSmoother(op, max_iterations=self.coarse_max_iterations,
+                                                 tolerance=self.coarse_tolerance)
+        else:
+            # coefficient -1: the convergent sign convention
+            op = HelmholtzOperator(-1.0, self.shift) if self.shift else LaplacianOperator(-1.0)
+            smoother = self._make_smoother()
+            coarse = GaussSeidelSmoother(max_iterations=self.coarse_max_iterations, tolerance=self.coarse_tolerance)
+        self._operator = op
         self._engine = CycleEngine(
-            grids, smoother=self._make_smoother(),
-            coarse_solver=GaussSeidelSmoother(max_iterations=self.coarse_max_iterations, tolerance=self.coarse_tolerance),
+            grids, smoother=smoother, coarse_solver=coarse,
             operators=[op] * L, restriction_ops=[RestrictionOperator("full_weighting")] * (L - 1),
             prolongation_ops=[ProlongationOperator("bilinear")] * (L - 1), cycle_type=self.cycle_type, pre=self.pre,
             post=self.post, kernels=self.kernels, loader=self.loader, device=dev)
@@ -208,20 +226,25 @@ class MixedPrecisionMultigrid:
         eng, g = self._engine, self._grid
         b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)
         ss = self._sumsq[1:2]
+        var = self.coefficient is not None
+        a64 = self._operator.coefficients(g.nx, g.ny, torch.float64) if var else None
         if ops.vc_aligned(b64.u, b64.f, b64.tmp, b32.u, b32.f) and eng.kernels != "basic":
             if with_update:
                 ops.vc_defect_pass(b64.u, b64.tmp, b64.f, g.hx, g.hy, e_in=b32.u, r_out=b32.f, sumsq_out=ss,
-                                   loader=eng.loader, shift=self.shift, workspace=eng.workspace, u_zero=u_zero)
+                                   loader=eng.loader, shift=self.shift, workspace=eng.workspace, u_zero=u_zero, a=a64)
                 b64.u, b64.tmp = b64.tmp, b64.u
             else:
                 ops.vc_defect_pass(b64.u, None, b64.f, g.hx, g.hy, r_out=b32.f, sumsq_out=ss, loader=eng.loader,
-                                   shift=self.shift, workspace=eng.workspace, u_zero=u_zero)
+                                   shift=self.shift, workspace=eng.workspace, u_zero=u_zero, a=a64)
         else:  # strict basic kernels
             if u_zero:
                 ops.zero_(b64.u)
             if with_update:
                 ops.axpy_(1.0, b32.u, b64.u)
-            ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp, shift=self.shift)
+            if var:
+                b64.tmp.copy_(self._operator.residual(g, b64.u, b64.f))
+            else:
+                ops.residual(b64.u, b64.f, g.hx, g.hy, -1.0, out=b64.tmp, shift=self.shift)
             ss.copy_(ops.sumsq_async(b64.tmp, slot=1))
             ops.cast(b64.tmp, torch.float32, out=b32.f)
 

@@ -82,9 +82,9 @@ def test_two_gpus_equal_one_gpu(tmp_path):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.xfail(strict=False, reason="peer-push halo transport (halo.py, torch symmetric memory): host logic proven on "
-                                        "CPU shared mappings, first run on NVLink hardware pending")
 def test_two_gpus_peer_push_halo_equals_one_gpu(tmp_path):
+    """One-sided ghost-row pushes over NVLink peer memory (halo.py) instead of NCCL send/recv: first run on hardware in
+    round 2 (2 x B200, profiles/r02_dist_2gpu_pytest.log), bit-identical to the single-GPU run; strict since."""
     out = str(tmp_path / "res.pt")
     script = os.path.join(ROOT, "tests", "dist_gpu_worker.py")
     for world, halo in ((1, "nccl"), (2, "p2p")):
