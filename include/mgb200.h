@@ -155,6 +155,20 @@ MG_API int mg_zero(void* x, int nx, int64_t ld, int dtype, void* stream);
  * tolerance although those values enter no equation, so the facade clears the ring of f. */
 MG_API int mg_zero_ring(void* x, int nx, int ny, int64_t ld, int first_row, int last_row, int dtype, void* stream);
 
+/* Right-hand side of one theta-method heat step in ONE pass over HBM (fp64): the linear system the reference documents,
+ *   (I - theta*dt*L_h) u^{n+1} = u^n + (1-theta)*dt*L_h u^n + dt*(theta f^{n+1} + (1-theta) f^n)
+ * (docs/methodology.md:710; L_h = alpha*lap_h, or div(a grad .) with a nodal field a), divided by theta*dt:
+ *   rhs = lam * (u + c_lap * L_h u + c_f1 * f1 + c_f0 * f0),
+ * L_h u taken as 0 on the first / last local row and column, the boundary ring zeroed (first / last row only when the
+ * flag says the slab touches the physical boundary), and sumsq_out[0] = sum of rhs^2 over rows [norm_row_lo,
+ * norm_row_hi) for the step's relative stopping test (`workspace`: mg_sumsq_workspace_doubles() doubles).  f1, f0, a
+ * may be NULL.  Replaces the eager copy / add / scale / norm sequence of the reference's time loop
+ * (applications/heat_solver.py:308-390) and of round 1's driver. */
+MG_API int mg_heat_rhs(const double* u, const double* f1, const double* f0, const double* a, double* rhs,
+                double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_u, int64_t ld_f1, int64_t ld_f0,
+                int64_t ld_a, int64_t ld_rhs, double hx, double hy, double c_lap, double c_f1, double c_f0, double lam,
+                int zero_first_row, int zero_last_row, int norm_row_lo, int norm_row_hi, void* stream);
+
 /* f[i][j] = amplitude * sin(kx*pi*x_i) * sin(ky*pi*y_j), x_i = x0 + i*(x1-x0)/(nx-1) evaluated in
  * fp64 and rounded to dtype (synthetic manufactured-solution data generated in HBM; the
  * README problem README.md:77-78 is amplitude = 2*pi^2, kx = ky = 1). */

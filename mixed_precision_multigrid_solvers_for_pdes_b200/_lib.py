@@ -39,6 +39,7 @@ SIGNATURES = {
     "mg_axpy": [_d, _p, _p, _i, _i, _l, _l, _i, _i, _p],
     "mg_zero": [_p, _i, _l, _i, _p],
     "mg_zero_ring": [_p, _i, _i, _l, _i, _i, _i, _p],
+    "mg_heat_rhs": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _l, _d, _d, _d, _d, _d, _d, _i, _i, _i, _i, _p],
     "mg_fill_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p],
     "mg_maxerr_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p, _p, _p],
     "mg_vc_workspace_doubles": [_i, _i],

@@ -56,12 +56,12 @@ class HeatSolver2D:
             return cfg.theta
         raise ValueError(f"Unknown time stepping method: {cfg.method}")
 
-    def _solver(self, nx, ny, domain, lam) -> MixedPrecisionMultigrid:
-        key = (nx, ny, tuple(domain), lam)
+    def _solver(self, nx, ny, domain, lam, coefficient=None) -> MixedPrecisionMultigrid:
+        key = (nx, ny, tuple(domain), lam, id(coefficient) if coefficient is not None else None)
         if self._mg is None or self._mg_key != key:
             self._mg = MixedPrecisionMultigrid(precision_strategy=self.precision_strategy, max_iterations=self.max_iterations,
                                                tolerance=self.tolerance, max_levels=self.max_levels,
-                                               cycle_type=self.cycle_type, shift=lam,
+                                               cycle_type=self.cycle_type, shift=lam, coefficient=coefficient,
                                                device=torch.device("cuda", self.device_id))
             self._mg.setup(nx, ny, domain)
             self._mg_key = key
@@ -69,17 +69,24 @@ class HeatSolver2D:
 
     def solve_heat_problem(self, problem: HeatProblem, nx: int, ny: int, time_config: TimeSteppingConfig,
                            save_solution_history: bool = False) -> Dict[str, Any]:
+        """`problem.thermal_diffusivity`: a number alpha (u_t = alpha*lap u + f, the reference's problem class) or a
+        callable a(X, Y) / an (nx, ny) array of nodal values (u_t = div(a grad u) + f, BASELINE configs[4]; README.md:175).
+        Per step ONE kernel forms the right-hand side in the solver's own buffer (mg_heat_rhs: scaled sum, ring, norm)
+        and the cycles run in place on the iterate, which never leaves the level-0 buffers of the cycle engine."""
+        if self.precision_strategy in ("single", "fp32"):
+            raise ValueError("the heat driver keeps the fp64 iterate between steps: use 'adaptive', 'refinement' or 'double'")
         dev = require_cuda(torch.device("cuda", self.device_id))
         domain = tuple(problem.domain)
         grid = Grid(nx, ny, domain)
-        alpha, theta = problem.thermal_diffusivity, self._theta(time_config)
-        u = empty_field(nx, ny, torch.float64, dev)
-        u.copy_(to_device(np.asarray(problem.initial_condition(grid.X, grid.Y), dtype=np.float64), device=dev)[0])
-        u[0, :] = 0
-        u[-1, :] = 0
-        u[:, 0] = 0
-        u[:, -1] = 0
-        rhs = empty_field(nx, ny, torch.float64, dev)
+        theta = self._theta(time_config)
+        diff = problem.thermal_diffusivity
+        variable = callable(diff) or isinstance(diff, (np.ndarray, torch.Tensor))
+        if variable:  # -div(a grad u) + lambda u, lambda = 1/(theta dt); the diffusivity sits in the operator
+            coef = np.array(np.broadcast_to(np.asarray(diff(grid.X, grid.Y) if callable(diff) else diff, dtype=np.float64),
+                                            (nx, ny)))
+            alpha = 1.0
+        else:
+            coef, alpha = None, float(diff)
 
         def source(t):
             if problem.source_function is None:
@@ -89,7 +96,12 @@ class HeatSolver2D:
 
         t_cur, dt, step = 0.0, time_config.dt, 0
         total_mg, solver_time = 0, 0.0
-        time_steps, solutions = [0.0], [to_host(u)] if save_solution_history else []
+        mg = self._solver(nx, ny, domain, 1.0 / (theta * alpha * dt), coef)
+        eng = mg._engine
+        b = eng.levels[0].bufs(torch.float64)
+        b.u.copy_(to_device(np.asarray(problem.initial_condition(grid.X, grid.Y), dtype=np.float64), device=dev)[0])
+        ops.zero_ring_(b.u)
+        time_steps, solutions = [0.0], [to_host(b.u)] if save_solution_history else []
         f_old = source(0.0) if theta < 1.0 else None
         t_start = time.time()
         while t_cur < time_config.t_final - 1e-14:
@@ -98,30 +110,30 @@ class HeatSolver2D:
             step += 1
             t_new = t_cur + dt
             lam = 1.0 / (theta * alpha * dt)
-            mg = self._solver(nx, ny, domain, lam)
+            nmg = self._solver(nx, ny, domain, lam, coef)
+            if nmg is not mg:  # shortened last step: another shift, hence another solver; hand the iterate over
+                u_prev = eng.levels[0].bufs(torch.float64).u
+                mg, eng = nmg, nmg._engine
+                eng.levels[0].bufs(torch.float64).u.copy_(u_prev)
             t0 = time.time()
-            # rhs = lambda * (u + (1-theta) alpha dt lap_h u + dt (theta f_new + (1-theta) f_old))
-            rhs.copy_(u)
-            if theta < 1.0:
-                rhs.add_(ops.apply_laplacian(u, grid.hx, grid.hy, 1.0), alpha=(1.0 - theta) * alpha * dt)
+            b = eng.levels[0].bufs(torch.float64)
+            a64 = mg._operator.coefficients(nx, ny, torch.float64) if variable else None
             f_new = source(t_new)
-            if f_new is not None:
-                rhs.add_(f_new, alpha=dt * theta)
-            if theta < 1.0 and f_old is not None:
-                rhs.add_(f_old, alpha=dt * (1.0 - theta))
-            rhs.mul_(lam)
+            # b.f = lambda * (u + (1-theta) dt L_h u + dt (theta f_new + (1-theta) f_old)), ring zeroed, norm: one kernel
+            ss = ops.heat_rhs_(b.u, b.f, grid.hx, grid.hy, lam=lam, c_lap=(1.0 - theta) * alpha * dt, f1=f_new,
+                               c_f1=dt * theta, f0=f_old if theta < 1.0 else None, c_f0=dt * (1.0 - theta), a=a64)
             # relative stopping test: the right-hand side scales with lambda
-            scale = float(np.sqrt(grid.hx * grid.hy * ops.sumsq(rhs)))
+            scale = float(np.sqrt(grid.hx * grid.hy * ops.read_scalar(ss)))
             mg.tolerance = self.tolerance * max(scale, 1e-300)
             mg.switch_threshold = max(1e-6 * scale, mg.tolerance)
-            u_new, info = mg.solve(PoissonProblem(rhs=rhs, nx=nx, ny=ny, domain=domain), initial_guess=u)
-            u.copy_(u_new)
+            _, info = mg._solve_device(True)  # cycles in place, from u^n
             solver_time += time.time() - t0
             total_mg += info["iterations"]
             f_old, t_cur = f_new, t_new
             if save_solution_history and step % time_config.save_frequency == 0:
                 time_steps.append(t_cur)
-                solutions.append(to_host(u))
+                solutions.append(to_host(eng.levels[0].bufs(torch.float64).u))
+        u = eng.levels[0].bufs(torch.float64).u
         total = time.time() - t_start
         u_host = to_host(u)
         errors: Dict[str, Any] = {}

@@ -339,6 +339,50 @@ __global__ void zero_ring_kernel(T* __restrict__ x, int nx, int ny, int64_t ld, 
   }
 }
 
+// Right-hand side of one theta-method heat step (docs/methodology.md:710 divided by theta*dt), ONE pass:
+//   rhs = lam * ( u + c_lap * L_h u + c_f1 * f1 + c_f0 * f0 ),   L_h = lap_h (a == null) or div(a grad .) (nodal a),
+// L_h u = 0 on the first / last local row and column (a slab's outer ghost rows lose one row of validity, like
+// mg_apply_laplacian), the boundary ring zeroed where the slab touches the physical boundary, and the sum of rhs^2 over
+// rows [row_lo, row_hi) (the relative stopping test of the step) as one partial per block.  Strict arithmetic.
+__global__ void __launch_bounds__(RED_THREADS)
+    heat_rhs_kernel(const double* __restrict__ u, const double* __restrict__ f1, const double* __restrict__ f0,
+                    const double* __restrict__ a, double* __restrict__ rhs, int nx, int ny, int64_t ldu, int64_t ldf1,
+                    int64_t ldf0, int64_t lda, int64_t ldr, double ihx2, double ihy2, double c_lap, double c_f1, double c_f0,
+                    double lam, int zero_first, int zero_last, int row_lo, int row_hi, double* __restrict__ partial) {
+  using A = Strict<double>;
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = blockIdx.x; i < nx; i += gridDim.x) {
+    const double* ur = u + (int64_t)i * ldu;
+    for (int j = threadIdx.x; j < ny; j += RED_THREADS) {
+      double t = ur[j];
+      if (c_lap != 0.0 && i > 0 && i < nx - 1 && j > 0 && j < ny - 1) {
+        double lap;
+        if (a != nullptr) {
+          const double* ar = a + (int64_t)i * lda + j;
+          const double ae = A::mul(0.5, A::add(ar[lda], ar[0])), aw = A::mul(0.5, A::add(ar[-lda], ar[0]));
+          const double an = A::mul(0.5, A::add(ar[1], ar[0])), as = A::mul(0.5, A::add(ar[-1], ar[0]));
+          const double x = A::mul(A::add(A::mul(ae, A::sub(ur[j + ldu], t)), A::mul(aw, A::sub(ur[j - ldu], t))), ihx2);
+          const double y = A::mul(A::add(A::mul(an, A::sub(ur[j + 1], t)), A::mul(as, A::sub(ur[j - 1], t))), ihy2);
+          lap = A::add(x, y);
+        } else {
+          const double x = A::mul(A::add(ur[j + ldu], ur[j - ldu]), ihx2), y = A::mul(A::add(ur[j + 1], ur[j - 1]), ihy2);
+          lap = A::sub(A::add(x, y), A::mul(t, A::add(A::mul(2.0, ihx2), A::mul(2.0, ihy2))));
+        }
+        t = A::add(t, A::mul(c_lap, lap));
+      }
+      if (f1 != nullptr) t = A::add(t, A::mul(c_f1, f1[(int64_t)i * ldf1 + j]));
+      if (f0 != nullptr) t = A::add(t, A::mul(c_f0, f0[(int64_t)i * ldf0 + j]));
+      t = A::mul(lam, t);
+      if (j == 0 || j == ny - 1 || (zero_first && i == 0) || (zero_last && i == nx - 1)) t = 0.0;
+      rhs[(int64_t)i * ldr + j] = t;
+      if (i >= row_lo && i < row_hi) acc += A::mul(t, t);
+    }
+  }
+  acc = block_reduce(acc, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
 void reduce_partials_sum(const double* partials, int n, double* out, cudaStream_t st) {
   final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(partials, n, out);
 }
@@ -650,6 +694,23 @@ int mg_zero_ring(void* x, int nx, int ny, int64_t ld, int first_row, int last_ro
   else
     zero_ring_kernel<float><<<(n + 255) / 256, 256, 0, st>>>((float*)x, nx, ny, ld, first_row, last_row);
   return check_launch("mg_zero_ring");
+}
+
+int mg_heat_rhs(const double* u, const double* f1, const double* f0, const double* a, double* rhs, double* sumsq_out,
+                double* workspace, int nx, int ny, int64_t ld_u, int64_t ld_f1, int64_t ld_f0, int64_t ld_a, int64_t ld_rhs,
+                double hx, double hy, double c_lap, double c_f1, double c_f0, double lam, int zero_first_row,
+                int zero_last_row, int norm_row_lo, int norm_row_hi, void* stream) {
+  MG_REQUIRE(u && rhs && sumsq_out && workspace && nx >= 3 && ny >= 3 && ld_u >= ny && ld_rhs >= ny && hx > 0 && hy > 0);
+  MG_REQUIRE((!f1 || ld_f1 >= ny) && (!f0 || ld_f0 >= ny) && (!a || ld_a >= ny) && rhs != u);
+  const int blocks = nx < RED_BLOCKS ? nx : RED_BLOCKS;
+  cudaStream_t st = as_stream(stream);
+  const double hx2 = pow(hx, 2.0), hy2 = pow(hy, 2.0);
+  heat_rhs_kernel<<<blocks, RED_THREADS, 0, st>>>(u, f1, f0, a, rhs, nx, ny, ld_u, ld_f1, ld_f0, ld_a, ld_rhs, 1.0 / hx2,
+                                                  1.0 / hy2, c_lap, f1 ? c_f1 : 0.0, f0 ? c_f0 : 0.0, lam, zero_first_row,
+                                                  zero_last_row, norm_row_lo < 0 ? 0 : norm_row_lo,
+                                                  (norm_row_hi < 0 || norm_row_hi > nx) ? nx : norm_row_hi, workspace);
+  final_reduce_kernel<false><<<1, RED_THREADS, 0, st>>>(workspace, blocks, sumsq_out);
+  return check_launch("mg_heat_rhs", 2);
 }
 
 int mg_fill_sinsin(void* f, int nx, int ny, int64_t ld, double x0, double x1, double y0, double y1,

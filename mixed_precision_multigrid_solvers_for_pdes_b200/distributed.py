@@ -167,6 +167,10 @@ class DeviceBackend:
     def zero_ring(self, t, first_row: bool, last_row: bool):
         self.ops.zero_ring_(t, first_row, last_row)
 
+    def heat_rhs(self, u, rhs, hx, hy, **k) -> torch.Tensor:
+        """One-kernel right-hand side of a theta-method step (mg_heat_rhs); returns sum(rhs^2) over `norm_rows`."""
+        return self.ops.heat_rhs_(u, rhs, hx, hy, **k).clone()
+
     def sumsq(self, t) -> torch.Tensor:
         """Sum of squares of a (row window of a) pitched field as a 1-element device tensor (no sync)."""
         return self.ops.sumsq_async(t, slot=2).clone()
@@ -692,13 +696,24 @@ class DistributedHeatSolver:
         y = domain[2] + np.arange(ny) * s.hy
         X, Y = np.meshgrid(x, y, indexing="ij")  # the slab's rows of Grid.X / Grid.Y (core/grid.py:50), ghosts included
 
+        EB = 64  # rows per callback call
+
         def evaluate(fn, *args):
-            """User callback on the slab, ONE GRID ROW PER CALL: vectorised libm routines may round the same argument
-            differently depending on its position in the array, so evaluating whole slabs would make the last bit
-            of the data depend on the number of ranks; a (1, ny) row looks the same on every decomposition."""
+            """User callback on the slab, in blocks of 64 grid rows ALIGNED TO THE GLOBAL ROW INDEX: vectorised libm
+            routines may round the same argument differently depending on its position in the array, so evaluating the
+            slab as a whole would make the last bit of the data depend on the number of ranks.  Every rank evaluates
+            the same global blocks [64 k, 64 k + 64) (whole blocks, clipped only at the end of the grid) and keeps its
+            rows: identical arrays go into the callback on every decomposition.  (Round 1 made one call per row:
+            8193 Python calls per field at configs[4].)"""
             out = np.empty(X.shape, dtype=np.float64)
-            for i in range(X.shape[0]):
-                out[i] = np.broadcast_to(np.asarray(fn(X[i:i + 1], Y[i:i + 1], *args), dtype=np.float64), (1, ny))[0]
+            g0, g1 = s.row0, s.row0 + s.loc_nx
+            for blk in range(g0 // EB, (g1 - 1) // EB + 1):
+                a0, a1 = blk * EB, min((blk + 1) * EB, s.nx_glob)
+                xb = domain[0] + np.arange(a0, a1) * s.hx
+                Xb, Yb = np.meshgrid(xb, y, indexing="ij")
+                vb = np.broadcast_to(np.asarray(fn(Xb, Yb, *args), dtype=np.float64), Xb.shape)
+                lo_, hi_ = max(a0, g0), min(a1, g1)
+                out[lo_ - g0:hi_ - g0] = vb[lo_ - a0:hi_ - a0]
             return out
 
         def to_slab(a, like):
@@ -735,24 +750,21 @@ class DistributedHeatSolver:
                 sol, eng = nsol, nsol.eng
             t0 = time.time()
             b = eng.bufs(0, torch.float64)
-            # rhs = lambda * (u + (1-theta) alpha dt lap_h u + dt (theta f_new + (1-theta) f_old)) on the local rows
+            # rhs = lambda * (u + (1-theta) alpha dt lap_h u + dt (theta f_new + (1-theta) f_old)) on the local rows, its
+            # boundary ring zeroed and the sum of squares of the owned rows: ONE kernel (mg_heat_rhs)
             v = eng.vdepth(b.u)
             if theta < 1.0:
                 eng.ensure(1, [(b.u, 0)])
                 v = eng.vdepth(b.u) - 1  # lap_h of a ghost row needs the next one
-            b.f.copy_(b.u)
-            if theta < 1.0:
-                b.f.add_(eng.be.apply_laplacian(b.u, s.hx, s.hy), alpha=(1.0 - theta) * alpha * dt)
             f_new = source(t_new)
-            if f_new is not None:
-                b.f.add_(to_slab(f_new, b.f), alpha=dt * theta)
-            if theta < 1.0 and f_old is not None:
-                b.f.add_(to_slab(f_old, b.f), alpha=dt * (1.0 - theta))
-            b.f.mul_(lam)
+            ss = eng.be.heat_rhs(b.u, b.f, s.hx, s.hy, lam=lam, c_lap=(1.0 - theta) * alpha * dt,
+                                 f1=to_slab(f_new, b.f) if f_new is not None else None, c_f1=dt * theta,
+                                 f0=to_slab(f_old, b.f) if (theta < 1.0 and f_old is not None) else None,
+                                 c_f0=dt * (1.0 - theta), zero_first_row=s.own_lo == 0,
+                                 zero_last_row=s.own_hi == s.nx_glob, norm_rows=(lo, hi))
             eng.set_valid(b.f, v)
-            sol.zero_boundary_ring_of_rhs()
             # relative stopping test against the GLOBAL rhs norm: the right-hand side scales with lambda
-            ss = eng.allreduce_sum(eng.be.sumsq(b.f[lo:hi]))
+            ss = eng.allreduce_sum(ss)
             scale = float(np.sqrt(s.hx * s.hy * float(ss.item())))
             sol.tolerance = self.tolerance * max(scale, 1e-300)
             sol.switch_threshold = max(1e-6 * scale, sol.tolerance)

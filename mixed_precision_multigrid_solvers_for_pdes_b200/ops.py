@@ -191,6 +191,28 @@ def zero_ring_(x: torch.Tensor, first_row: bool = True, last_row: bool = True) -
     return x
 
 
+def heat_rhs_(u: torch.Tensor, rhs: torch.Tensor, hx: float, hy: float, *, lam: float, c_lap: float = 0.0,
+              f1: Optional[torch.Tensor] = None, c_f1: float = 0.0, f0: Optional[torch.Tensor] = None, c_f0: float = 0.0,
+              a: Optional[torch.Tensor] = None, zero_first_row: bool = True, zero_last_row: bool = True,
+              norm_rows: Optional[Tuple[int, int]] = None, slot: int = 3) -> torch.Tensor:
+    """rhs = lam * (u + c_lap * L_h u + c_f1 * f1 + c_f0 * f0) with the boundary ring zeroed, in one pass (mg_heat_rhs);
+    returns a 1-element device view holding sum(rhs^2) over `norm_rows` (no sync)."""
+    for t in (u, rhs, f1, f0, a):
+        if t is not None and t.dtype != torch.float64:
+            raise TypeError("heat_rhs_: fp64 fields")
+    nx, ny = u.shape
+    w = _workspace(u.device)
+    n = w.numel() - 8
+    out = w[n + slot:n + slot + 1]
+    lo, hi = norm_rows if norm_rows is not None else (0, -1)
+    _lib.call("mg_heat_rhs", u.data_ptr(), f1.data_ptr() if f1 is not None else None,
+              f0.data_ptr() if f0 is not None else None, a.data_ptr() if a is not None else None, rhs.data_ptr(),
+              out.data_ptr(), w.data_ptr(), nx, ny, ld(u), ld(f1) if f1 is not None else 0, ld(f0) if f0 is not None else 0,
+              ld(a) if a is not None else 0, ld(rhs), hx, hy, float(c_lap), float(c_f1), float(c_f0), float(lam),
+              1 if zero_first_row else 0, 1 if zero_last_row else 0, lo, hi, stream_ptr())
+    return out
+
+
 def fill_sinsin_(f: torch.Tensor, domain=(0.0, 1.0, 0.0, 1.0), amplitude: float = 1.0, kx: float = 1.0,
                  ky: float = 1.0) -> torch.Tensor:
     nx, ny = f.shape

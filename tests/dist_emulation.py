@@ -59,6 +59,27 @@ class OracleBackend:
     def apply_laplacian(self, u, hx, hy):
         return torch.from_numpy(O.apply_laplacian(_np(u), hx, hy, 1.0))
 
+    def heat_rhs(self, u, rhs, hx, hy, *, lam, c_lap=0.0, f1=None, c_f1=0.0, f0=None, c_f0=0.0, a=None,
+                 zero_first_row=True, zero_last_row=True, norm_rows=None):
+        U = _np(u)
+        t = U.copy()
+        if c_lap != 0.0:
+            t = t + c_lap * O.apply_laplacian(U, hx, hy, 1.0)  # 0 on the local first / last rows and columns
+        if f1 is not None:
+            t = t + c_f1 * _np(f1)
+        if f0 is not None:
+            t = t + c_f0 * _np(f0)
+        t = lam * t
+        t[:, 0] = 0
+        t[:, -1] = 0
+        if zero_first_row:
+            t[0, :] = 0
+        if zero_last_row:
+            t[-1, :] = 0
+        rhs.copy_(torch.from_numpy(t))
+        lo, hi = norm_rows if norm_rows is not None else (0, t.shape[0])
+        return torch.tensor([float(np.sum(t[lo:hi] ** 2))], dtype=torch.float64)
+
     def vc_pass(self, u_in, u_out, f, hx, hy, *, sweeps=2, omega=1.0, coefficient=-1.0, coarse_in=None,
                 coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0, workspace=None):
         F = _np(f)

@@ -82,3 +82,69 @@ def test_heat_with_source_matches_analytical_solution():
     assert res["errors"]["relative_max_error"] < 3e-4
     assert len(res["solution_history"]) == 5 and res["time_steps"][-1] == pytest.approx(0.2)
     assert 1 <= res["avg_mg_iterations"] <= 12
+
+
+def test_heat_rhs_kernel_equals_the_eager_formula():
+    """mg_heat_rhs: lam*(u + c_lap*L_h u + c_f1*f1 + c_f0*f0), ring zeroed, sum of squares -- one pass -- against NumPy,
+    for lap_h and for div(a grad .)."""
+    rng = np.random.default_rng(61)
+    n, m = 129, 65
+    g = Grid(n, m, (0.0, 2.0, 0.0, 1.0))
+    u, f1, f0 = (rng.uniform(-1, 1, (n, m)) for _ in range(3))
+    a = 1.0 + 0.5 * rng.uniform(0, 1, (n, m))
+    du, d1, d0, da = (to_device(t)[0] for t in (u, f1, f0, a))
+    for coef in (None, a):
+        lap = np.zeros_like(u)
+        if coef is None:
+            lap[1:-1, 1:-1] = ((u[2:, 1:-1] + u[:-2, 1:-1]) / g.hx ** 2 + (u[1:-1, 2:] + u[1:-1, :-2]) / g.hy ** 2
+                               - u[1:-1, 1:-1] * (2 / g.hx ** 2 + 2 / g.hy ** 2))
+        else:
+            lap = -O.varcoef_apply(u, a, g.hx, g.hy, 0.0)
+        want = 7.5 * (u + 0.3 * lap + 0.2 * f1 + 0.1 * f0)
+        want[0, :] = want[-1, :] = want[:, 0] = want[:, -1] = 0.0
+        out = empty_field(n, m, np.float64)
+        ss = ops.heat_rhs_(du, out, g.hx, g.hy, lam=7.5, c_lap=0.3, f1=d1, c_f1=0.2, f0=d0, c_f0=0.1,
+                           a=da if coef is not None else None, norm_rows=(3, n - 5))
+        got = to_host(out)
+        assert np.max(np.abs(got - want)) <= 1e-12 * np.max(np.abs(want))
+        assert abs(ss.item() - float(np.sum(got[3:n - 5] ** 2))) <= 1e-12 * float(np.sum(got ** 2))
+    # backward Euler without sources: a pure scaling, slab flags leave the first / last row alone
+    out = empty_field(n, m, np.float64)
+    ops.heat_rhs_(du, out, g.hx, g.hy, lam=2.0, zero_first_row=False, zero_last_row=False)
+    want = 2.0 * u
+    want[:, 0] = want[:, -1] = 0.0
+    assert np.array_equal(to_host(out), want)
+
+
+def test_heat_with_variable_diffusivity_converges_in_time_and_space():
+    """u_t = div(a grad u) + f with a manufactured solution u = exp(-t) sin(pi x) sin(pi y) (BASELINE configs[4], the
+    variable-coefficient half; no reference operator): backward Euler is O(dt) + O(h^2)."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import HeatProblem
+
+    def a(X, Y):
+        return 1.0 + 0.5 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) + X * Y
+
+    def exact(X, Y, t):
+        return np.exp(-t) * np.sin(np.pi * X) * np.sin(np.pi * Y)
+
+    def source(X, Y, t):
+        sx, cx, sy, cy = np.sin(np.pi * X), np.cos(np.pi * X), np.sin(np.pi * Y), np.cos(np.pi * Y)
+        ax = np.pi * np.cos(2 * np.pi * X) * np.cos(np.pi * Y) + Y
+        ay = -0.5 * np.pi * np.sin(2 * np.pi * X) * np.sin(np.pi * Y) + X
+        div = (ax * np.pi * cx * sy + ay * np.pi * sx * cy) - a(X, Y) * 2 * np.pi ** 2 * sx * sy
+        return np.exp(-t) * (-sx * sy - div)
+
+    prob = HeatProblem("varcoef_mms", lambda X, Y: exact(X, Y, 0.0), source, exact, thermal_diffusivity=a)
+    errs = {}
+    for n, steps in ((65, 8), (65, 16), (129, 64)):
+        T = 0.05
+        res = HeatSolver2D(tolerance=1e-10).solve_heat_problem(
+            prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, T / steps, T))
+        assert res["total_steps"] == steps
+        errs[(n, steps)] = res["errors"]["max_error"]
+    assert 1.6 < errs[(65, 8)] / errs[(65, 16)] < 2.2, errs          # first order in time
+    assert errs[(129, 64)] < 0.3 * errs[(65, 16)], errs              # dt/4 and h/2: error / 4 (within 20 %)
+    # Crank-Nicolson on the same problem: the explicit half goes through the div(a grad .) branch of mg_heat_rhs
+    cn = HeatSolver2D(tolerance=1e-10).solve_heat_problem(
+        prob, 129, 129, TimeSteppingConfig(TimeSteppingMethod.CRANK_NICOLSON, 0.05 / 8, 0.05))
+    assert cn["errors"]["max_error"] < errs[(129, 64)]
