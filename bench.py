@@ -68,6 +68,9 @@ def parse():
     ap.add_argument("--strong", action="store_true",
                     help="multi-GPU: --n is the GLOBAL grid (n x n on the unit square) split into row slabs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--varcoef", action="store_true",
+                    help="1-GPU arm: the variable-coefficient operator -div(a grad u), a = 1 + 0.5 sin(2 pi x) cos(pi y) + x y "
+                         "(the operator of BASELINE configs[4]) through the mg_vcv_* passes; use with --n 8193")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     return ap.parse_args()
 
@@ -333,10 +336,14 @@ def gpu_arm(a):
         return
 
     from mixed_precision_multigrid_solvers_for_pdes_b200.solvers.policy import CONTINUE
+    coefficient = None
+    if a.varcoef:
+        coefficient = lambda X, Y: 1.0 + 0.5 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) + X * Y  # noqa: E731
+        a.no_e2e = True  # no closed-form solution for this operator: the e2e leg's error check has nothing to check
     solver = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
                                      cycle_type=a.cycle, loader=a.loader, max_iterations=10 ** 9, device=dev,
-                                     smoother=a.smoother,
-                                     use_cuda_graphs=not a.no_graphs)
+                                     smoother="red_black_gauss_seidel" if a.varcoef else a.smoother,
+                                     use_cuda_graphs=not a.no_graphs, coefficient=coefficient)
     solver.setup(n, n)
     eng, g = solver._engine, solver._grid
     b64 = eng.levels[0].bufs(torch.float64)
@@ -427,6 +434,8 @@ def gpu_arm(a):
         px, py = (int(v) for v in dims.split("x"))
         pts = px * py
         w = 8 if dt == "f64" else 4
+        if name.startswith("var:"):       # variable coefficients: + the nodal coefficient row, once per pass
+            return alg_bytes(name[4:] + "/" + dt + "/" + dims) + w * pts
         if name.startswith("small"):      # whole coarse sub-cycle in shared memory: read f (+u), write u
             return 2.0 * w * pts
         if "resid32" in name or "update" in name:
@@ -528,7 +537,8 @@ def gpu_arm(a):
         "dtype": "f32 cycle / f64 iterate+residual" if solver.mode in ("switch", "refine") else
                  ("f64" if solver.mode == "fp64" else "f32"),
         "data": "synthetic",
-        "config": {"workload": f"2D Poisson {n}x{n} manufactured sin*sin, {a.cycle}(2,2) "
+        "config": {"workload": ("2D variable-coefficient -div(a grad u) = f " if a.varcoef else "2D Poisson ") +
+                               f"{n}x{n} manufactured sin*sin, {a.cycle}(2,2) "
                                f"{'red-black GS' if a.smoother == 'rbgs' else 'damped Jacobi (2/3)'}, "
                                f"precision_strategy={a.strategy} (BASELINE configs[2])", "levels": eng.num_levels,
                    "loader": a.loader, "cuda_graphs": (not a.no_graphs), "graphs_captured": replayed, "priming_solves": primed,

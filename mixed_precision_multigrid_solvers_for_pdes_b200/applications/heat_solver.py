@@ -126,9 +126,13 @@ class HeatSolver2D:
             scale = float(np.sqrt(grid.hx * grid.hy * ops.read_scalar(ss)))
             mg.tolerance = self.tolerance * max(scale, 1e-300)
             mg.switch_threshold = max(1e-6 * scale, mg.tolerance)
+            t1 = time.time()
             _, info = mg._solve_device(True)  # cycles in place, from u^n
             solver_time += time.time() - t0
+            self.rhs_time = getattr(self, "rhs_time", 0.0) + (t1 - t0)
+            self.cycle_time = getattr(self, "cycle_time", 0.0) + info["cycle_time"]
             total_mg += info["iterations"]
+            self.last_precisions = info["precision_history"]
             f_old, t_cur = f_new, t_new
             if save_solution_history and step % time_config.save_frequency == 0:
                 time_steps.append(t_cur)

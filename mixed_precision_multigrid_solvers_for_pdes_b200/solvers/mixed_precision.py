@@ -151,7 +151,7 @@ class MixedPrecisionMultigrid:
                 raise ValueError("variable coefficients are smoothed with red-black Gauss-Seidel")
             a = self.coefficient(g.X, g.Y) if callable(self.coefficient) else self.coefficient
             if not isinstance(a, torch.Tensor):
-                a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (nx, ny)))
+                a = np.array(np.broadcast_to(np.asarray(a, dtype=np.float64), (nx, ny)))  # owned, writable copy
             op = VariableCoefficientOperator(a, self.shift)
             smoother = VariableCoefficientSmoother(op, relaxation_parameter=self.damping_factor)
             coarse = VariableCoefficientSmoother(op, max_iterations=self.coarse_max_iterations,

@@ -49,6 +49,7 @@ if world > 1:
 else:
     s = HeatSolver2D(tolerance=1e-8)
     s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 3))  # warm-up: graphs captured
+    s.rhs_time = s.cycle_time = 0.0
     t0 = time.time()
     res = s.solve_heat_problem(prob, n, n, cfg)
     wall = time.time() - t0
@@ -60,7 +61,9 @@ if rank == 0:
                       "ms_per_step": round(1e3 * res["total_solver_time"] / steps, 3),
                       "avg_mg_cycles_per_step": res["avg_mg_iterations"], "max_error": res["errors"].get("max_error"),
                       "relative_max_error": res["errors"].get("relative_max_error"),
-                      "halo_exchanges": res.get("halo_exchanges")}))
+                      "halo_exchanges": res.get("halo_exchanges"),
+                      "rhs_s": round(getattr(s, "rhs_time", 0.0), 3), "cycles_s": round(getattr(s, "cycle_time", 0.0), 3),
+                      "precision_history_last_step": getattr(s, "last_precisions", None)}))
 if world > 1:
     del s, res
     import gc
