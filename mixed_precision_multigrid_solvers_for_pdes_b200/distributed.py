@@ -179,7 +179,8 @@ class DeviceBackend:
         """lap_h(u) on the interior of the local array, 0 on its first/last rows and columns."""
         return self.ops.apply_laplacian(u, hx, hy, 1.0)
 
-    def make_coarse_engine(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0):
+    def make_coarse_engine(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0,
+                           coefficient=None):
         from .core.grid import Grid
         from .operators.laplacian import HelmholtzOperator, LaplacianOperator
         from .operators.transfer import ProlongationOperator, RestrictionOperator
@@ -189,9 +190,17 @@ class DeviceBackend:
         for _ in range(1, levels):
             grids.append(grids[-1].coarsen())
         L = len(grids)
-        op = HelmholtzOperator(-1.0, shift) if shift else LaplacianOperator(-1.0)
-        eng = CycleEngine(grids, smoother=GaussSeidelSmoother(red_black=True),
-                          coarse_solver=GaussSeidelSmoother(max_iterations=coarse_max, tolerance=coarse_tol),
+        if coefficient is not None:  # the full coarse coefficient field, identical on every rank
+            from .operators.variable import VariableCoefficientOperator, VariableCoefficientSmoother
+            with torch.cuda.device(self.device):
+                op = VariableCoefficientOperator(np.ascontiguousarray(coefficient, dtype=np.float64), shift)
+            smoother = VariableCoefficientSmoother(op)
+            coarse = VariableCoefficientSmoother(op, max_iterations=coarse_max, tolerance=coarse_tol)
+        else:
+            op = HelmholtzOperator(-1.0, shift) if shift else LaplacianOperator(-1.0)
+            smoother = GaussSeidelSmoother(red_black=True)
+            coarse = GaussSeidelSmoother(max_iterations=coarse_max, tolerance=coarse_tol)
+        eng = CycleEngine(grids, smoother=smoother, coarse_solver=coarse,
                           operators=[op] * L, restriction_ops=[RestrictionOperator()] * max(0, L - 1),
                           prolongation_ops=[ProlongationOperator()] * max(0, L - 1), cycle_type=cycle_type, pre=pre,
                           post=post, kernels="auto", loader=self.loader, device=self.device)
@@ -226,7 +235,7 @@ class DistributedCycleEngine:
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), num_levels: Optional[int] = None,
                  cycle_type: str = "V", pre: int = 2, post: int = 2, agglomerate_below: int = 1025,
                  dist_levels: Optional[int] = None, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
-                 shift: float = 0.0, backend=None, group=None, device=None, transport=None):
+                 shift: float = 0.0, backend=None, group=None, device=None, transport=None, coefficient=None):
         if not (1 <= pre <= 2 and 1 <= post <= 2):
             raise ValueError("the distributed engine runs 1 or 2 pre/post sweeps per pass")
         if not shift >= 0.0:
@@ -254,10 +263,17 @@ class DistributedCycleEngine:
         self.transport = transport
         self._bufs: Dict[Tuple[int, torch.dtype], _Bufs] = {}
         self.valid: Dict[int, int] = {}  # data_ptr -> number of ghost rows per side that currently hold exact values
+        # variable coefficients: -div(a grad u) + shift*u with a callable a(X, Y) (or a full (nx, ny) array), SURVEY 8f-1.
+        # Every level evaluates / slices its own slab rows (ghost rows included: the field is static, it never needs an
+        # exchange); the agglomerated levels get the full coarse field on every rank.
+        self.coefficient = coefficient
+        self._coef: Dict[Tuple[int, torch.dtype], torch.Tensor] = {}
         an, am = self.part.agg_shape
+        ckw = {"shift": self.shift} if self.shift else {}
+        if coefficient is not None:
+            ckw["coefficient"] = self._coef_rows(self.D, 0, an)
         self.coarse = self.be.make_coarse_engine(an, am, self.domain, num_levels - self.D, cycle_type, pre, post,
-                                                 coarse_tolerance, coarse_max_iterations,
-                                                 **({"shift": self.shift} if self.shift else {}))
+                                                 coarse_tolerance, coarse_max_iterations, **ckw)
         self._kw = {"shift": self.shift} if self.shift else {}  # forwarded to every slab pass
         self.exchanges = 0
 
@@ -281,6 +297,49 @@ class DistributedCycleEngine:
         for b, u, tmp in roles:
             b.u, b.tmp = u, tmp
         self.valid = dict(valid)
+
+    # -- variable coefficients -----------------------------------------------------------------------------
+    def _coef_rows(self, l: int, r0: int, r1: int) -> np.ndarray:
+        """Nodal coefficient values of global rows [r0, r1) of level l (fp64 NumPy).  A callable is evaluated in blocks
+        of 64 rows aligned to the global row index (identical arrays enter it on every decomposition, so the values
+        do not depend on the number of ranks: see DistributedHeatSolver.evaluate); an array is sliced with the
+        level's stride (injection, like VariableCoefficientOperator.coefficients)."""
+        nxl, nyl = (self.nx - 1) // 2 ** l + 1, (self.ny - 1) // 2 ** l + 1
+        c = self.coefficient
+        if not callable(c):
+            full = c.detach().cpu().numpy() if isinstance(c, torch.Tensor) else np.asarray(c, dtype=np.float64)
+            st = 2 ** l
+            return np.ascontiguousarray(full[::st, ::st][r0:r1], dtype=np.float64)
+        hx = (self.domain[1] - self.domain[0]) / (self.nx - 1) * 2 ** l
+        hy = (self.domain[3] - self.domain[2]) / (self.ny - 1) * 2 ** l
+        y = self.domain[2] + np.arange(nyl) * hy
+        out = np.empty((r1 - r0, nyl), dtype=np.float64)
+        EB = 64
+        for blk in range(r0 // EB, (r1 - 1) // EB + 1):
+            a0, a1 = blk * EB, min((blk + 1) * EB, nxl)
+            Xb, Yb = np.meshgrid(self.domain[0] + np.arange(a0, a1) * hx, y, indexing="ij")
+            vb = np.broadcast_to(np.asarray(c(Xb, Yb), dtype=np.float64), Xb.shape)
+            lo_, hi_ = max(a0, r0), min(a1, r1)
+            out[lo_ - r0:hi_ - r0] = vb[lo_ - a0:hi_ - a0]
+        if not (out > 0).all():
+            raise ValueError("the diffusion coefficient must be positive")
+        return out
+
+    def coef(self, l: int, dtype) -> Optional[torch.Tensor]:
+        """Coefficient slab of distributed level l (None for the constant-coefficient operator)."""
+        if self.coefficient is None:
+            return None
+        t = self._coef.get((l, dtype))
+        if t is None:
+            s = self.part.slab(l)
+            t = self.be.empty(s.loc_nx, s.ny, dtype)
+            t.copy_(torch.from_numpy(self._coef_rows(l, s.row0, s.row0 + s.loc_nx)).to(t.device))
+            self._coef[(l, dtype)] = t
+        return t
+
+    def _var_kw(self, l: int, dtype) -> Dict[str, Any]:
+        a = self.coef(l, dtype)
+        return dict(self._kw, a=a) if a is not None else dict(self._kw)
 
     # -- buffers ------------------------------------------------------------------------------------------
     def bufs(self, l: int, dtype) -> _Bufs:
@@ -403,27 +462,48 @@ class DistributedCycleEngine:
         b, c = self.bufs(l, dtype), self.bufs(l + 1, dtype)
         off, rows = self.part.coarse_view(l)
         G = self.part.ghost
-        # down: `pre` sweeps + residual + restriction; dependency cone of the owned coarse rows = 2*pre + 2 fine rows
-        ins = [(b.f, l)] + ([] if u_zero else [(b.u, l)])
-        self.ensure(2 * self.pre + 2, ins)
-        v = min(self.vdepth(t) for t, _ in ins)
-        self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.pre, coefficient=-1.0, coarse_out=c.f[off:off + rows],
-                        u_zero=u_zero, **self._kw)
-        b.u, b.tmp = b.tmp, b.u
-        self.set_valid(b.u, v - 2 * self.pre)
-        self.set_valid(c.f, (v - (2 * self.pre + 2)) // 2)
+        kw = self._var_kw(l, dtype)
+        # sweeps per HBM pass: 2, except fp64 variable-coefficient passes (one sweep: register budget of the kernel)
+        ms = 1 if (self.coefficient is not None and dtype == torch.float64) else 2
+        # down: `pre` sweeps, the last pass with residual + restriction; dependency cone of a pass = 2 rows per sweep
+        # (+2 for the owned coarse rows of the restriction)
+        n, uz = self.pre, u_zero
+        while n > 0:
+            k = min(n, ms)
+            last = n - k == 0
+            ins = [(b.f, l)] + ([] if uz else [(b.u, l)])
+            self.ensure(2 * k + (2 if last else 0), ins)
+            v = min(self.vdepth(t) for t, _ in ins)
+            self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=k, coefficient=-1.0,
+                            coarse_out=c.f[off:off + rows] if last else None, u_zero=uz, **kw)
+            b.u, b.tmp = b.tmp, b.u
+            self.set_valid(b.u, v - 2 * k)
+            if last:
+                self.set_valid(c.f, (v - (2 * k + 2)) // 2)
+            n -= k
+            uz = False
         for rep in range(self._reps(l)):
             self.cycle(dtype, l + 1, u_zero=(rep == 0))
-        # up: prolongation + `post` sweeps (+ norm): cone 2*post (+1); the prolongation of a coarse field with v_c
-        # valid ghost rows is exact on 2*v_c - 1 fine ghost rows
+        # up: prolongation in the first pass, `post` sweeps (+ norm in the last): cone 2 rows per sweep (+1); the
+        # prolongation of a coarse field with v_c valid ghost rows is exact on 2*v_c - 1 fine ghost rows
         norm = sumsq_out is not None and l == 0
-        self.ensure(2 * self.post + (1 if norm else 0), [(b.u, l), (b.f, l), (c.u, l + 1)],
-                    effective=lambda d: min(d[0], d[1], 2 * d[2] - 1))
-        v = min(self.vdepth(b.u), self.vdepth(b.f), 2 * self.vdepth(c.u) - 1)
-        self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=self.post, coefficient=-1.0, coarse_in=c.u[off:off + rows],
-                        sumsq_out=sumsq_out if norm else None, norm_rows=s.own_local, **self._kw)
-        b.u, b.tmp = b.tmp, b.u
-        self.set_valid(b.u, v - 2 * self.post)
+        n, first = self.post, True
+        while n > 0:
+            k = min(n, ms)
+            last = n - k == 0
+            items = [(b.u, l), (b.f, l)] + ([(c.u, l + 1)] if first else [])
+            eff = (lambda d: min(d[0], d[1], 2 * d[2] - 1)) if first else None
+            self.ensure(2 * k + (1 if (norm and last) else 0), items, effective=eff)
+            v = min(self.vdepth(b.u), self.vdepth(b.f))
+            if first:
+                v = min(v, 2 * self.vdepth(c.u) - 1)
+            self.be.vc_pass(b.u, b.tmp, b.f, s.hx, s.hy, sweeps=k, coefficient=-1.0,
+                            coarse_in=c.u[off:off + rows] if first else None,
+                            sumsq_out=sumsq_out if (norm and last) else None, norm_rows=s.own_local, **kw)
+            b.u, b.tmp = b.tmp, b.u
+            self.set_valid(b.u, v - 2 * k)
+            n -= k
+            first = False
 
     # -- data movement helpers -----------------------------------------------------------------------------------
     def scatter_rows(self, dst: torch.Tensor, full_rows_fn, l: int = 0) -> None:
@@ -570,7 +650,7 @@ class DistributedMixedPrecisionSolver:
     def _launch_defect(self, with_update: bool, u_zero: bool = False) -> None:
         eng, s = self.eng, self.s0
         b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
-        kw = dict(eng._kw)
+        kw = eng._var_kw(0, torch.float64)
         if u_zero:
             kw["u_zero"] = True
         self.ss.zero_()
@@ -671,24 +751,31 @@ class DistributedHeatSolver:
             return cfg.theta
         raise ValueError(f"Unknown time stepping method: {cfg.method}")
 
-    def _solver(self, nx, ny, domain, lam) -> "DistributedMixedPrecisionSolver":
-        key = (nx, ny, tuple(domain), lam)
+    def _solver(self, nx, ny, domain, lam, coefficient=None) -> "DistributedMixedPrecisionSolver":
+        key = (nx, ny, tuple(domain), lam, id(coefficient) if coefficient is not None else None)
         sol = self._solvers.get(key)
         if sol is None:
+            kw = dict(self.engine_kw)
+            if coefficient is not None:
+                kw["coefficient"] = coefficient
             sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=self.precision_strategy,
                                                   tolerance=self.tolerance, max_iterations=self.max_iterations,
                                                   cycle_type=self.cycle_type, shift=lam, backend=self.backend,
                                                   device=self.device, use_cuda_graphs=self.use_cuda_graphs,
-                                                  **self.engine_kw)
+                                                  **kw)
             self._solvers[key] = sol
         return sol
 
     def solve_heat_problem(self, problem, nx: int, ny: int, time_config, gather: bool = True) -> Dict[str, Any]:
         import time
         domain = tuple(float(v) for v in problem.domain)
-        alpha, theta = float(problem.thermal_diffusivity), self._theta(time_config)
+        theta = self._theta(time_config)
+        diff = problem.thermal_diffusivity
+        # a number alpha: u_t = alpha lap u + f; a callable a(X, Y) / an (nx, ny) array: u_t = div(a grad u) + f
+        coef = diff if (callable(diff) or isinstance(diff, (np.ndarray, torch.Tensor))) else None
+        alpha = 1.0 if coef is not None else float(diff)
         dt, t_cur, step, total_mg = float(time_config.dt), 0.0, 0, 0
-        sol = self._solver(nx, ny, domain, 1.0 / (theta * alpha * dt))
+        sol = self._solver(nx, ny, domain, 1.0 / (theta * alpha * dt), coef)
         eng, s = sol.eng, sol.s0
         G = eng.part.ghost
         lo, hi = s.own_local
@@ -742,7 +829,7 @@ class DistributedHeatSolver:
             step += 1
             t_new = t_cur + dt
             lam = 1.0 / (theta * alpha * dt)
-            nsol = self._solver(nx, ny, domain, lam)
+            nsol = self._solver(nx, ny, domain, lam, coef)
             if nsol is not sol:  # shortened last step: another shift, hence another solver; hand the iterate over
                 nb = nsol.eng.bufs(0, torch.float64)
                 nb.u.copy_(eng.bufs(0, torch.float64).u)
@@ -761,7 +848,8 @@ class DistributedHeatSolver:
                                  f1=to_slab(f_new, b.f) if f_new is not None else None, c_f1=dt * theta,
                                  f0=to_slab(f_old, b.f) if (theta < 1.0 and f_old is not None) else None,
                                  c_f0=dt * (1.0 - theta), zero_first_row=s.own_lo == 0,
-                                 zero_last_row=s.own_hi == s.nx_glob, norm_rows=(lo, hi))
+                                 zero_last_row=s.own_hi == s.nx_glob, norm_rows=(lo, hi),
+                                 **({"a": eng.coef(0, torch.float64)} if coef is not None else {}))
             eng.set_valid(b.f, v)
             # relative stopping test against the GLOBAL rhs norm: the right-hand side scales with lambda
             ss = eng.allreduce_sum(ss)

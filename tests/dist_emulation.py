@@ -13,11 +13,32 @@ def _np(t):
     return t.numpy()
 
 
+def _varcoef_cycle(u, f, a, hx, hy, shift, lvl, levels, cycle_type, pre, post, ctol, cmax):
+    """The recursion of solvers/multigrid.py:253-337 for -div(a grad u) + shift*u with the oracle's operators
+    (coefficients of coarser levels by injection, coarsest level: red-black GS sweeps to tolerance)."""
+    if lvl == levels - 1:
+        for _ in range(cmax):
+            u = O.varcoef_rbgs_smooth(u, f, a, hx, hy, 1.0, 1, shift)
+            if O.l2_norm(O.varcoef_residual(u, f, a, hx, hy, shift), hx, hy) < ctol:
+                break
+        return u
+    u = O.varcoef_rbgs_smooth(u, f, a, hx, hy, 1.0, pre, shift)
+    rc = O.restrict(O.varcoef_residual(u, f, a, hx, hy, shift))
+    ec = np.zeros_like(rc)
+    for _ in range({"V": 1, "W": 2}[cycle_type]):
+        ec = _varcoef_cycle(ec, rc, np.ascontiguousarray(a[::2, ::2]), 2 * hx, 2 * hy, shift, lvl + 1, levels, cycle_type,
+                            pre, post, ctol, cmax)
+    u = u + O.prolong(ec)
+    return O.varcoef_rbgs_smooth(u, f, a, hx, hy, 1.0, post, shift)
+
+
 class _CoarseEmu:
-    def __init__(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0):
+    def __init__(self, nx, ny, domain, levels, cycle_type, pre, post, coarse_tol, coarse_max, shift=0.0,
+                 coefficient=None):
         self.args = dict(max_levels=levels, cycle_type=cycle_type, pre=pre, post=post, coarse_tolerance=coarse_tol,
                          coarse_max_iterations=coarse_max, domain=domain, shift=shift)
         self.nx, self.ny = nx, ny
+        self.coefficient = None if coefficient is None else np.asarray(coefficient, dtype=np.float64)
         self._b = {}
 
     def bufs(self, dtype):
@@ -33,6 +54,16 @@ class _CoarseEmu:
     def cycle(self, dtype, u_zero):
         b = self.bufs(dtype)
         npdt = np.float64 if dtype == torch.float64 else np.float32
+        if self.coefficient is not None:  # variable coefficients: every level in the level dtype (emulation only)
+            A = self.args
+            dom = A["domain"]
+            hx, hy = (dom[1] - dom[0]) / (self.nx - 1), (dom[3] - dom[2]) / (self.ny - 1)
+            u0 = np.zeros_like(_np(b.u)) if u_zero else _np(b.u).copy()
+            u = _varcoef_cycle(u0, _np(b.f).copy(), self.coefficient.astype(npdt), npdt(hx), npdt(hy), npdt(A["shift"]), 0,
+                               A["max_levels"], A["cycle_type"], A["pre"], A["post"], A["coarse_tolerance"],
+                               min(A["coarse_max_iterations"], 200))
+            b.u.copy_(torch.from_numpy(np.ascontiguousarray(u)).to(dtype))
+            return b.u
         s = O.OracleMultigrid(self.nx, self.ny, dtype=npdt, **self.args)
         L = len(s.grids)
         s.level_dtypes = [npdt] * (L - 1) + [np.float64]
@@ -63,7 +94,9 @@ class OracleBackend:
                  zero_first_row=True, zero_last_row=True, norm_rows=None):
         U = _np(u)
         t = U.copy()
-        if c_lap != 0.0:
+        if c_lap != 0.0 and a is not None:
+            t = t - c_lap * O.varcoef_apply(U, _np(a), hx, hy, 0.0)  # div(a grad u); 0 on the local ring
+        elif c_lap != 0.0:
             t = t + c_lap * O.apply_laplacian(U, hx, hy, 1.0)  # 0 on the local first / last rows and columns
         if f1 is not None:
             t = t + c_f1 * _np(f1)
@@ -81,7 +114,7 @@ class OracleBackend:
         return torch.tensor([float(np.sum(t[lo:hi] ** 2))], dtype=torch.float64)
 
     def vc_pass(self, u_in, u_out, f, hx, hy, *, sweeps=2, omega=1.0, coefficient=-1.0, coarse_in=None,
-                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0, workspace=None):
+                coarse_out=None, sumsq_out=None, u_zero=False, norm_rows=None, rows=0, shift=0.0, workspace=None, a=None):
         F = _np(f)
         nx = F.shape[0]
         nxo = nx if nx % 2 == 1 else nx - 1
@@ -89,11 +122,16 @@ class OracleBackend:
         if coarse_in is not None:
             C = _np(coarse_in)[:(nxo - 1) // 2 + 1]
             U[:nxo] += O.prolong(C)
-        U = O.rbgs_smooth(U, F, hx, hy, omega, sweeps, shift)
+        dt = F.dtype.type
+        if a is not None:
+            U = O.varcoef_rbgs_smooth(U, F, _np(a), dt(hx), dt(hy), dt(omega), sweeps, dt(shift))
+        else:
+            U = O.rbgs_smooth(U, F, hx, hy, omega, sweeps, shift)
         if u_out is not None:
             u_out.copy_(torch.from_numpy(U))
         if coarse_out is not None or sumsq_out is not None:
-            R = O.residual(U, F, hx, hy, coefficient, shift)
+            R = (O.varcoef_residual(U, F, _np(a), dt(hx), dt(hy), dt(shift)) if a is not None
+                 else O.residual(U, F, hx, hy, coefficient, shift))
             if coarse_out is not None:
                 rc = O.restrict(R[:nxo])
                 coarse_out[:rc.shape[0]].copy_(torch.from_numpy(rc))
@@ -102,13 +140,14 @@ class OracleBackend:
                 sumsq_out[0] = float(np.sum(R[lo:hi].astype(np.float64) ** 2))
 
     def vc_defect_pass(self, u_in, u_out, f, hx, hy, *, e_in=None, r_out=None, sumsq_out=None, coefficient=-1.0,
-                       norm_rows=None, rows=0, shift=0.0, workspace=None, u_zero=False):
+                       norm_rows=None, rows=0, shift=0.0, workspace=None, u_zero=False, a=None):
         U = np.zeros_like(_np(f)) if u_zero else _np(u_in).copy()
         if e_in is not None:
             U = U + _np(e_in).astype(np.float64)
             u_out.copy_(torch.from_numpy(U))
         if r_out is not None:
-            R = O.residual(U, _np(f), hx, hy, coefficient, shift)
+            R = (O.varcoef_residual(U, _np(f), _np(a), hx, hy, shift) if a is not None
+                 else O.residual(U, _np(f), hx, hy, coefficient, shift))
             r_out.copy_(torch.from_numpy(R.astype(np.float32)))
             lo, hi = norm_rows if norm_rows is not None else (0, U.shape[0])
             sumsq_out[0] = float(np.sum(R[lo:hi] ** 2))

@@ -68,9 +68,11 @@ def _worker(rank, world, port, case, out):
         if case.get("shm_dir"):
             from mixed_precision_multigrid_solvers_for_pdes_b200.halo import FileShmTransport
             transport = FileShmTransport(case["shm_dir"], GHOST)
+        coef = (lambda X, Y: 1.0 + 0.5 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) + 0.25 * X * Y) if case.get("varcoef") else None
         if case["kind"] == "cycle":
             eng = DistributedCycleEngine(nx, ny, domain=dom, cycle_type=case["cycle"], agglomerate_below=case["agg"],
-                                         backend=OracleBackend(), transport=transport)
+                                         backend=OracleBackend(), transport=transport, coefficient=coef,
+                                         shift=case.get("shift", 0.0))
             b = eng.bufs(0, torch.float64)
             s = eng.part.slab(0)
             b.f.copy_(torch.from_numpy(f[s.row0:s.row0 + s.loc_nx]))
@@ -95,7 +97,7 @@ def _worker(rank, world, port, case, out):
         else:
             sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=case["strategy"],
                                                   tolerance=1e-8, agglomerate_below=case["agg"], backend=OracleBackend(),
-                                                  transport=transport)
+                                                  transport=transport, coefficient=coef)
             sol.set_rhs_from_global(f)
             u, info = sol.solve()
             res = {"norms": info["residual_history"], "u": sol.eng.gather_solution(u).numpy(), "D": sol.eng.D,
@@ -146,6 +148,22 @@ def test_two_rank_fp64_cycles_equal_single_process_reference(tmp_path, cycle):
     u, info = s.solve(f)
     assert np.array_equal(r2["u"], u)                       # owned rows bit-identical to the 1-process run
     np.testing.assert_allclose(r2["norms"], info["residual_history"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("strategy", ["double", "adaptive"])
+def test_two_ranks_equal_one_rank_with_variable_coefficients(tmp_path, strategy):
+    """-div(a grad u) + shift*u on slabs: coefficient slabs evaluated per level in globally aligned blocks,
+    fp64 passes of one sweep (2 passes per smoothing step, each with its own ghost-validity bookkeeping), the full coarse
+    coefficient field on the agglomerated levels.  2 ranks == 1 rank bit for bit, same cycle counts."""
+    case = dict(kind="solve", nx=257, ny=129, domain=(0.0, 2.0, 0.0, 1.0), agg=33, strategy=strategy, varcoef=True)
+    r2, r1 = _run(2, case, tmp_path), _run(1, case, tmp_path)
+    assert r2["D"] == r1["D"] >= 2 and r2["ex"] > 0
+    assert len(r2["norms"]) == len(r1["norms"]) <= 14 and r1["norms"][-1] < 1e-8
+    assert np.array_equal(r2["u"], r1["u"])
+    np.testing.assert_allclose(r2["norms"], r1["norms"], rtol=1e-12)
+    cyc = dict(kind="cycle", nx=257, ny=129, domain=(0.0, 2.0, 0.0, 1.0), cycle="W", agg=33, cycles=2, varcoef=True, shift=25.0)
+    c2, c1 = _run(2, cyc, tmp_path), _run(1, cyc, tmp_path)
+    assert np.array_equal(c2["u"], c1["u"])
 
 
 def test_four_ranks_equal_one_rank(tmp_path):

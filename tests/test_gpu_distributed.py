@@ -98,3 +98,24 @@ def test_two_gpus_peer_push_halo_equals_one_gpu(tmp_path):
     for key in ("double", "adaptive", "adaptive_graphs"):
         assert r1[key]["iterations"] == r2[key]["iterations"]
         assert np.array_equal(r1[key]["u"], r2[key]["u"]), key
+
+
+def test_world1_distributed_variable_coefficients_match_the_single_gpu_facade():
+    """-div(a grad u) on row slabs (world = 1: slab passes, coefficient slabs per level, agglomerated coarse engine with the
+    full coarse field) against MixedPrecisionMultigrid(coefficient=...): same cycle counts, same solution to rounding
+    (the facade injects the coarse coefficients from its fine-grid evaluation, the slabs evaluate every level)."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MixedPrecisionMultigrid, PoissonProblem
+    from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedMixedPrecisionSolver
+    n = 513
+    coef = lambda X, Y: 1.0 + 0.5 * np.sin(2 * np.pi * X) * np.cos(np.pi * Y) + X * Y  # noqa: E731
+    f = O.mms_rhs(n)
+    f[0, :] = f[-1, :] = f[:, 0] = f[:, -1] = 0.0
+    for strategy in ("double", "adaptive"):
+        sol = DistributedMixedPrecisionSolver(n, n, precision_strategy=strategy, tolerance=1e-8, agglomerate_below=65,
+                                              device=torch.device("cuda", 0), coefficient=coef)
+        sol.set_rhs_from_global(torch.from_numpy(f).cuda())
+        u, info = sol.solve()
+        us, si = MixedPrecisionMultigrid(strategy, coefficient=coef, tolerance=1e-8).solve(PoissonProblem(rhs=f, nx=n, ny=n))
+        assert info["converged"] and info["iterations"] == si["iterations"], (info["iterations"], si["iterations"])
+        np.testing.assert_allclose(info["residual_history"], si["residual_history"], rtol=1e-6)
+        assert np.max(np.abs(u.cpu().numpy() - us)) <= 1e-11 * np.max(np.abs(us))
