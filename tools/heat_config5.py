@@ -5,7 +5,7 @@ multigrid solve per step.  Prints a JSON line (time per step, MG cycles per step
                                                                                   u_t = div(a grad u), a = 1 + 0.5 sin(2 pi x) cos(pi y) + x y
                                                                                   (the variable-coefficient half of configs[4])
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
-        tools/heat_config5.py [n] [steps]                                         N GPUs, row slabs (DistributedHeatSolver)
+        tools/heat_config5.py [n] [steps] [varcoef]                               N GPUs, row slabs (DistributedHeatSolver)
 """
 import json
 import os
@@ -37,7 +37,7 @@ if world > 1:
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     s = DistributedHeatSolver(tolerance=1e-8, device=dev, use_cuda_graphs=True)
-    s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 3), gather=False)  # warm-up: graphs captured
+    s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 8), gather=False)  # warm-up: graphs captured
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.time()
@@ -48,7 +48,7 @@ if world > 1:
     rank = dist.get_rank()
 else:
     s = HeatSolver2D(tolerance=1e-8)
-    s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 3))  # warm-up: graphs captured
+    s.solve_heat_problem(prob, n, n, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt, dt * 8))  # warm-up: graphs captured
     s.rhs_time = s.cycle_time = 0.0
     t0 = time.time()
     res = s.solve_heat_problem(prob, n, n, cfg)
