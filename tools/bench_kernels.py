@@ -89,6 +89,30 @@ def main():
                             fn, byt, sw = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=2, coarse_in=ec, **jk)), 3.25 * w, 2
                         else:
                             continue
+                    elif mode.startswith("v") and mode[1:] in ("smooth1", "smooth2", "zdown2", "zdown1", "up2", "up1", "defect") \
+                            and loader == "tma":
+                        # variable coefficients -div(a grad u): the nodal field rides along (+1 word per point)
+                        if "acoef" not in locals() or acoef.dtype != dt:
+                            acoef = empty_field(n, n, dt)
+                            acoef.copy_(1.0 + torch.rand((n, n), generator=gen, device="cuda", dtype=dt))
+                        m = mode[1:]
+                        if m == "defect":
+                            if dn != "f64":
+                                continue
+                            e32 = empty_field(n, n, torch.float32); r32 = empty_field(n, n, torch.float32)
+                            fn = (lambda: ops.vc_defect_pass(u, out, f, h, h, e_in=e32, r_out=r32, sumsq_out=ss, a=acoef, rows=rows))
+                            byt, sw = 40.0, 0
+                        else:
+                            sw = int(m[-1])
+                            if dn == "f64" and sw > 1:
+                                continue
+                            if m.startswith("smooth"):
+                                fn, byt = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=sw, a=acoef, rows=rows)), 4 * w
+                            elif m.startswith("zdown"):
+                                fn, byt = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=sw, coarse_out=rc, u_zero=True, a=acoef,
+                                                               rows=rows)), 3.25 * w
+                            else:
+                                fn, byt = (lambda: ops.vc_pass(u, out, f, h, h, sweeps=sw, coarse_in=ec, a=acoef, rows=rows)), 4.25 * w
                     elif mode == "resrestrict":
                         fn, byt, sw = (lambda: ops.vc_pass(u, None, f, h, h, sweeps=0, coarse_out=rc, **kw)), 2.25 * w, 0
                     else:
