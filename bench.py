@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
                     help="multi-GPU ghost exchange: grouped NCCL send/recv (default) or one-sided pushes over NVLink peer "
                          "memory (halo.py; opt-in until measured)")
+    ap.add_argument("--ghost", type=int, default=None,
+                    help="multi-GPU: ghost rows per interior side (even, >= 6; default: distributed.BENCH_GHOST).  Deeper "
+                         "ghosts = fewer halo exchanges per cycle (every pass spends 2 rows of validity per sweep)")
     ap.add_argument("--strong", action="store_true",
                     help="multi-GPU: --n is the GLOBAL grid (n x n on the unit square) split into row slabs")
     ap.add_argument("--no-e2e", action="store_true")

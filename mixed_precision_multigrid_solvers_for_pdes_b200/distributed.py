@@ -29,6 +29,8 @@ import torch
 import torch.distributed as dist
 
 GHOST = 8  # ghost rows per interior side on every distributed level (even; >= 6 = cone of a fused pass)
+# bench.py's default (--ghost): measured on 8 B200 (profiles/r02_bench_8gpu_ghost*.json), see DESIGN.md section 6
+BENCH_GHOST = 8
 
 
 # ======================================================================================================
@@ -235,7 +237,8 @@ class DistributedCycleEngine:
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), num_levels: Optional[int] = None,
                  cycle_type: str = "V", pre: int = 2, post: int = 2, agglomerate_below: int = 1025,
                  dist_levels: Optional[int] = None, coarse_tolerance: float = 1e-12, coarse_max_iterations: int = 1000,
-                 shift: float = 0.0, backend=None, group=None, device=None, transport=None, coefficient=None):
+                 shift: float = 0.0, backend=None, group=None, device=None, transport=None, coefficient=None,
+                 ghost: Optional[int] = None):
         if not (1 <= pre <= 2 and 1 <= post <= 2):
             raise ValueError("the distributed engine runs 1 or 2 pre/post sweeps per pass")
         if not shift >= 0.0:
@@ -251,11 +254,16 @@ class DistributedCycleEngine:
             while (a - 1) % 2 == 0 and (b - 1) % 2 == 0 and (a - 1) // 2 + 1 >= 5 and (b - 1) // 2 + 1 >= 5:
                 a, b, num_levels = (a - 1) // 2 + 1, (b - 1) // 2 + 1, num_levels + 1
         self.num_levels = num_levels
+        # ghost rows per interior side (even, >= 6 = dependency cone of a fused 2-sweep pass with restriction).  Deeper
+        # ghosts buy fewer exchanges: every pass spends 2 rows of validity per sweep, restriction halves what is left
+        ghost = GHOST if ghost is None else int(ghost)
+        if ghost < 6 or ghost % 2:
+            raise ValueError("ghost must be even and >= 6")
         if dist_levels is None:
-            dist_levels = choose_dist_levels(nx, ny, self.world, num_levels, agglomerate_below)
+            dist_levels = choose_dist_levels(nx, ny, self.world, num_levels, agglomerate_below, ghost)
         if dist_levels >= num_levels:
             dist_levels = num_levels - 1  # the coarsest level is always solved on the gathered grid
-        self.part = SlabPartition(nx, ny, self.world, self.rank, num_levels, max(1, dist_levels), domain)
+        self.part = SlabPartition(nx, ny, self.world, self.rank, num_levels, max(1, dist_levels), domain, ghost)
         self.D = self.part.dist_levels
         self.be = backend if backend is not None else DeviceBackend(device)
         # optional one-sided halo transport (halo.py): slab arrays in symmetric memory, ghost rows pushed into the
@@ -912,7 +920,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
                                           device=dev, use_cuda_graphs=not a.no_graphs,
                                           **({"agglomerate_below": a.agg} if getattr(a, "agg", None) else {}),
-                                          **_halo_kw(a, dev))
+                                          ghost=getattr(a, "ghost", None) or BENCH_GHOST, **_halo_kw(a, dev))
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
     sol.eng.exchange(sol.eng.bufs(0, torch.float64).f, 0)
@@ -993,6 +1001,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     e2e = None
     if not a.no_e2e:
         b64 = sol.eng.bufs(0, torch.float64)
+        numa = bind_to_gpu_numa_node(dev)  # before the pinned slabs are allocated (first touch decides the node)
         f_host = torch.empty((s0.loc_nx, ny), dtype=torch.float64, pin_memory=True)
         u_host = torch.empty((s0.loc_nx, ny), dtype=torch.float64, pin_memory=True)
         f_host.copy_(b64.f)
@@ -1015,7 +1024,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                "h2d_bytes_per_step": s0.loc_nx * ny * 8 * world, "d2h_bytes_per_step": s0.loc_nx * ny * 8 * world,
                "step": "one distributed solve(): every rank uploads its pinned host slab of f and downloads its slab of u",
                "seconds_per_solve": float(tt.item()) / reps, "iterations": info["iterations"],
-               "final_residual": info["final_residual"]}
+               "final_residual": info["final_residual"], "numa": numa}
     clocks = clk.summary()
     return {
         "metric": _metric_name(), "value": value, "unit": "unknowns/s", "n_gpus": world, "steps": a.steps,
@@ -1025,7 +1034,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
         "config": {"workload": f"2D Poisson {nx}x{ny} ({(nx - 1) // world} rows per GPU) manufactured sin*sin on "
                                f"({domain[0]:g},{domain[1]:g})x(0,1), "
                                f"{a.cycle}(2,2) red-black GS, precision_strategy={a.strategy}, row slabs over {world} GPUs",
-                   "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": GHOST,
+                   "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": sol.eng.part.ghost,
                    "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
                    "halo_exchanges_per_step": ex_per_step, "halo": getattr(a, "halo", "nccl"),
                    "cuda_graphs": (not a.no_graphs),
@@ -1077,7 +1086,36 @@ def _halo_kw(a, dev) -> Dict[str, Any]:
     if getattr(a, "halo", "nccl") != "p2p":
         return {}
     from .halo import SymmMemTransport
-    return {"transport": SymmMemTransport(dev, GHOST)}
+    return {"transport": SymmMemTransport(dev, getattr(a, "ghost", None) or BENCH_GHOST)}
+
+
+def bind_to_gpu_numa_node(dev) -> Dict[str, Any]:
+    """Pin this process to the CPU cores NVML reports as local to its GPU, so that pinned host buffers allocated (first
+    touched) afterwards live on the GPU's NUMA node.  With one process per GPU all sharing the default affinity, every
+    rank's staging memory otherwise lands on one socket and the host <-> device copies of 8 ranks share its memory
+    controllers and PCIe root (round 1: 15 GB/s per rank).  Best effort: returns what it did."""
+    import os
+    info: Dict[str, Any] = {"bound": False}
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[idx])
+        h = nv.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        info.update({"gpu_local_cpus": len(local), "allowed_cpus": len(allowed), "usable": len(use)})
+        if use and len(use) < len(allowed):
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+    except Exception as exc:  # no NVML, no permission, ...
+        info["error"] = str(exc)[:120]
+    return info
 
 
 def _metric_name() -> str:
