@@ -61,7 +61,8 @@ def parse():
                     help="grid of the CPU sample; default: 8193 for the cpu_baseline leg of the GPU arm (bounded to "
                          "~10 s), the configured --n for --impl reference when the host has the memory for it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--agg", type=int, default=None, help="multi-GPU: agglomerate levels with <= this many points per side")
+    ap.add_argument("--agg", type=int, default=None,
+                    help="multi-GPU: agglomerate levels with <= this many points per side (default: distributed.BENCH_AGG)")
     ap.add_argument("--halo", default="nccl", choices=["nccl", "p2p"],
                     help="multi-GPU ghost exchange: grouped NCCL send/recv (default) or one-sided pushes over NVLink peer "
                          "memory (halo.py; opt-in until measured)")

@@ -29,8 +29,11 @@ import torch
 import torch.distributed as dist
 
 GHOST = 8  # ghost rows per interior side on every distributed level (even; >= 6 = cone of a fused pass)
-# bench.py's default (--ghost): measured on 8 B200 (profiles/r02_bench_8gpu_ghost*.json), see DESIGN.md section 6
-BENCH_GHOST = 8
+# bench.py's defaults (--ghost, --agg), measured on 8 B200 (profiles/r02_bench_8gpu*.json):
+# ghost 8 / 16 / 32 -> 5.9 / 3.9 / 1.9 exchanges and 3.90 / 3.85 / 3.80 ms per cycle; agglomerating at 513 instead of 1025
+# points per side (4097 x 513 instead of 8193 x 1025 solved redundantly) -> 3.71 ms
+BENCH_GHOST = 32
+BENCH_AGG = 513
 
 
 # ======================================================================================================
@@ -919,7 +922,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     sol = DistributedMixedPrecisionSolver(nx, ny, domain=domain, precision_strategy=a.strategy, switch_threshold=1e-6,
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
                                           device=dev, use_cuda_graphs=not a.no_graphs,
-                                          **({"agglomerate_below": a.agg} if getattr(a, "agg", None) else {}),
+                                          agglomerate_below=_bench_agg(a),
                                           ghost=getattr(a, "ghost", None) or BENCH_GHOST, **_halo_kw(a, dev))
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
@@ -1062,11 +1065,13 @@ def _bench_parity_check(a, world: int, rank: int, dev, n: int = 4097) -> Dict[st
     ops.zero_ring_(f)
     dsol = DistributedMixedPrecisionSolver(n, n, precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
                                            cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader), device=dev,
-                                           use_cuda_graphs=False, **_halo_kw(a, dev))
+                                           use_cuda_graphs=False, agglomerate_below=_bench_agg(a),
+                                           ghost=getattr(a, "ghost", None) or BENCH_GHOST, **_halo_kw(a, dev))
     dsol.set_rhs_from_global(f)
     u, info = dsol.solve()
     full = dsol.eng.gather_solution(u)
-    out: Dict[str, Any] = {"grid": [n, n], "cycles_distributed": info["iterations"], "dist_levels": dsol.eng.D}
+    out: Dict[str, Any] = {"grid": [n, n], "cycles_distributed": info["iterations"], "dist_levels": dsol.eng.D,
+                           "ghost_rows": dsol.eng.part.ghost}
     if rank == 0:
         single = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
                                          cycle_type=a.cycle, loader=a.loader, device=dev, strict_reference_norm=True)
@@ -1080,6 +1085,12 @@ def _bench_parity_check(a, world: int, rank: int, dev, n: int = 4097) -> Dict[st
     torch.cuda.synchronize()
     dist.barrier()
     return out
+
+
+def _bench_agg(a) -> int:
+    """V-cycles agglomerate at BENCH_AGG; a W / F cycle visits level l 2^l times, so every extra distributed level
+    multiplies its exchanges: those keep the engine's default (1025)."""
+    return getattr(a, "agg", None) or (BENCH_AGG if getattr(a, "cycle", "V") == "V" else 1025)
 
 
 def _halo_kw(a, dev) -> Dict[str, Any]:
