@@ -91,7 +91,12 @@ MG_API int mg_smooth_jacobi(void* u, void* tmp, const void* f, int nx, int ny, i
  * wavefronts by ONE thread block (identical arithmetic to the sequential sweep).
  * mode 0: forward sweeps  -- GaussSeidelSmoother(red_black=False).smooth, solvers/smoothers.py:153-173;
  * mode 1: backward sweeps (i, j descending)  -- _backward_sweep, solvers/smoothers.py:268-284;
- * mode 2: each sweep = forward then backward  -- SymmetricGaussSeidelSmoother.smooth, :246-266. */
+ * mode 2: each sweep = forward then backward  -- SymmetricGaussSeidelSmoother.smooth, :246-266.
+ * PERFORMANCE: a lexicographic sweep is a chain of nx + ny - 3 dependent wavefronts; one block walks them with a block
+ * barrier each (~0.3 us per wavefront: ~0.6 ms per sweep at 1025^2, one SM busy).  It exists for parity with the
+ * reference's setup default and as the coarsest-level solver; use the red-black smoother (mg_vc_pass) on fine levels.
+ * A multi-block version would pay a grid-wide barrier (2-3 us) per wavefront, or per tile-diagonal of a blocked
+ * wavefront with the same inner chain per tile: neither beats the single block at these sizes. */
 #define MG_LEXGS_FORWARD 0
 #define MG_LEXGS_BACKWARD 1
 #define MG_LEXGS_SYMMETRIC 2

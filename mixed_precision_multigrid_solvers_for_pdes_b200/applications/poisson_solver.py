@@ -102,3 +102,36 @@ class PoissonSolver2D:
             e = np.array([r["errors"][key] for r in rows])
             out[f"{key}_rate"] = float(np.polyfit(np.log(hs), np.log(e), 1)[0])
         return out
+
+    def benchmark_solver_performance(self, problem: PoissonProblem, grid_sizes, num_runs: int = 5) -> Dict[str, Any]:
+        """Wall-clock statistics of repeated solves per grid size (poisson_solver.py:398-460: same arguments, same
+        result keys; `throughput` = unknowns per second of a whole solve, as there)."""
+        rows = []
+        for nx, ny in grid_sizes:
+            times, iters = [], []
+            for _ in range(num_runs):
+                r = self.solve_poisson_problem(problem, nx, ny)
+                times.append(r["solve_time"])
+                iters.append(r["solver_info"]["iterations"])
+            avg = float(np.mean(times))
+            rows.append({"grid_size": (nx, ny), "total_unknowns": nx * ny, "num_runs": num_runs, "avg_time": avg,
+                         "std_time": float(np.std(times)), "min_time": float(min(times)), "max_time": float(max(times)),
+                         "avg_iterations": float(np.mean(iters)), "throughput": nx * ny / avg,
+                         "solver_type": self.solver_type})
+        return {"problem_name": problem.name,
+                "solver_configuration": {"solver_type": self.solver_type, "use_gpu": self.use_gpu,
+                                         "mixed_precision": self.enable_mixed_precision, "max_levels": self.max_levels,
+                                         "cycle_type": self.cycle_type},
+                "benchmark_results": rows}
+
+    def get_solver_statistics(self) -> Dict[str, Any]:
+        """poisson_solver.py:462-480."""
+        stats: Dict[str, Any] = {
+            "solver_type": self.solver_type,
+            "configuration": {"max_levels": self.max_levels, "max_iterations": self.max_iterations,
+                              "tolerance": self.tolerance, "cycle_type": self.cycle_type, "use_gpu": self.use_gpu,
+                              "mixed_precision": self.enable_mixed_precision},
+            "solve_history_count": len(self.solve_history)}
+        if hasattr(self.solver, "get_performance_statistics"):
+            stats["performance_statistics"] = self.solver.get_performance_statistics()
+        return stats

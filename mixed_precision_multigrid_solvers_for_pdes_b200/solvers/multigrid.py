@@ -35,12 +35,16 @@ class MultigridSolver(BaseSolver):
                  cycle_type: str = MultigridCycle.V_CYCLE, pre_smooth_iterations: int = 2,
                  post_smooth_iterations: int = 2, coarse_tolerance: float = 1e-12,
                  coarse_max_iterations: int = 1000, verbose: bool = False, kernels: str = "auto", loader: str = "tma",
-                 device=None):
+                 device=None, use_cuda_graphs: bool = True):
         super().__init__(max_iterations, tolerance, verbose, "Multigrid")
         self.max_levels, self.cycle_type = max_levels, cycle_type
         self.pre_smooth_iterations, self.post_smooth_iterations = pre_smooth_iterations, post_smooth_iterations
         self.coarse_tolerance, self.coarse_max_iterations = coarse_tolerance, coarse_max_iterations
         self.kernels, self.loader, self.device = kernels, loader, device
+        # A cycle is ~3 launches per level, most of them microseconds long: without a precision manager (whose decisions
+        # happen on the host between levels) each (dtype, buffer-role state) is captured once and replayed (graphs.py)
+        self.use_cuda_graphs = use_cuda_graphs
+        self._graphs = None
         self.grids: List = []
         self.operators: List = []
         self.restriction_ops: List = []
@@ -82,6 +86,9 @@ class MultigridSolver(BaseSolver):
                                   pre=self.pre_smooth_iterations, post=self.post_smooth_iterations,
                                   kernels=self.kernels, loader=self.loader, device=self.device)
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.engine.dev)
+        from .graphs import GraphCache
+        self._graphs = GraphCache(self.engine.buffer_state, self.engine.snapshot_roles, CycleEngine.restore_roles,
+                                  self.use_cuda_graphs)
 
     # -- solve (multigrid.py:184-251) ------------------------------------------------------------------
     def _level_dtypes(self, base_dtype, precision_manager) -> List[torch.dtype]:
@@ -135,8 +142,14 @@ class MultigridSolver(BaseSolver):
                     ops.cast(b_old.u, dts[0], out=b_new.u)
                     b_new.f.copy_(f_in)
                 cur_dtype = dts[0]
-            fused_norm = eng.cycle(dts, 0, precision_manager, sumsq_out=self._sumsq)
-            ss = self._sumsq if fused_norm else eng.residual_sumsq_async(cur_dtype)
+            if precision_manager is None and self.use_cuda_graphs and self._graphable(dts):
+                # fused levels + native coarse solve: no host synchronisation inside the cycle -> CUDA-graph replay
+                self._graphs.enabled = True
+                self._graphs.run(f"cycle:{dts[0]}", lambda: eng.cycle(dts, 0, None, sumsq_out=self._sumsq))
+                ss = self._sumsq
+            else:
+                fused_norm = eng.cycle(dts, 0, precision_manager, sumsq_out=self._sumsq)
+                ss = self._sumsq if fused_norm else eng.residual_sumsq_async(cur_dtype)
             residual_norm = float(np.sqrt(hxhy * ss.item()))
             prec = precision_manager.current_precision.value if precision_manager else "double"
             self.history.record_iteration(residual_norm, time.time() - t0, prec, 0)
@@ -149,6 +162,30 @@ class MultigridSolver(BaseSolver):
         u = eng.levels[0].bufs(cur_dtype).u
         out = like_input(u, was_np) if was_np else u.clone()
         return out, self.get_convergence_info()
+
+    def _graphable(self, dts) -> bool:
+        """A cycle can be captured when every level runs fused passes (or the small-cycle kernel) and the coarsest
+        solve is the one-launch native one: nothing in it synchronises with the host."""
+        eng = self.engine
+        key = tuple(str(d) for d in dts)
+        hit = getattr(self, "_graphable_cache", {}).get(key)
+        if hit is not None:
+            return hit
+        L = eng.num_levels
+        # level 0 must be a fused pass: it is the one that leaves the residual norm in `_sumsq`
+        ok = getattr(eng.coarse_solver, "kind", None) in ("lexgs", "rbgs_var") and L >= 2 and not eng._small_ok(0, dts)
+        for lvl in range(L - 1):
+            if not ok or eng._small_ok(lvl, dts):
+                break
+            try:
+                if not eng._fusable(lvl, dts):
+                    ok = False
+                    break
+            except ValueError:
+                ok = False
+                break
+        self._graphable_cache = dict(getattr(self, "_graphable_cache", {}), **{key: ok})
+        return ok
 
     def apply_cycles(self, rhs, num_cycles: int = 1, initial_guess=None):
         """`num_cycles` cycles on A u = rhs from `initial_guess` (zero by default) with NO residual norms and no host

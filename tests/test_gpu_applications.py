@@ -53,3 +53,19 @@ def test_multigrid_preconditioner_is_fixed_cycles_from_zero():
     for _ in range(6):
         u = u + pc.apply(O.residual(u, x, g.hx, g.hy, -1.0))
     assert np.linalg.norm(O.residual(u, x, g.hx, g.hy, -1.0)[1:-1, 1:-1]) < 1e-6 * np.linalg.norm(x)
+
+
+def test_poisson_solver_2d_benchmark_and_statistics_keys():
+    """poisson_solver.py:398-480: same result keys."""
+    prob = PoissonTestProblems().get_problem("trigonometric")
+    ps = PoissonSolver2D(solver_type="gpu_multigrid")
+    b = ps.benchmark_solver_performance(prob, [(65, 65), (129, 129)], num_runs=2)
+    assert b["problem_name"] == prob.name and set(b["solver_configuration"]) == {"solver_type", "use_gpu", "mixed_precision",
+                                                                                 "max_levels", "cycle_type"}
+    assert [r["grid_size"] for r in b["benchmark_results"]] == [(65, 65), (129, 129)]
+    for r in b["benchmark_results"]:
+        assert set(r) == {"grid_size", "total_unknowns", "num_runs", "avg_time", "std_time", "min_time", "max_time",
+                          "avg_iterations", "throughput", "solver_type"}
+        assert r["avg_iterations"] == 8 and r["throughput"] > 0
+    st = ps.get_solver_statistics()
+    assert st["solve_history_count"] == 4 and st["configuration"]["tolerance"] == 1e-8

@@ -142,3 +142,31 @@ def test_default_operator_sign_diverges_like_reference():
     _, info = s.solve(g, op, O.mms_rhs(33))
     h = info["residual_history"]
     assert not info["converged"] and abs(h[0] - 23.8) < 0.2 and h[-1] > 10 * h[0] and h[5] > h[4] > h[3]
+
+
+def test_drop_in_solver_replays_cuda_graphs_bit_identically(solve_golden, golden_meta):
+    """MultigridSolver.solve (the drop-in class) replays its cycles as CUDA graphs when nothing in them synchronises with
+    the host; results equal the eager run and the reference's golden run bit for bit."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import (GaussSeidelSmoother, Grid, LaplacianOperator,
+                                                                 MultigridSolver, ProlongationOperator,
+                                                                 RestrictionOperator)
+    n = 257
+    g = Grid(n, n)
+    op = LaplacianOperator(-1.0)
+    f = O.mms_rhs(n)
+    outs = []
+    for graphs in (False, True):
+        s = MultigridSolver(max_levels=7, max_iterations=30, tolerance=1e-8, use_cuda_graphs=graphs)
+        s.setup(g, op, RestrictionOperator(), ProlongationOperator(), smoother=GaussSeidelSmoother(red_black=True))
+        u, info = s.solve(g, op, f)
+        u2, info2 = s.solve(g, op, f)          # second solve: every cycle replays
+        assert info["residual_history"] == info2["residual_history"] and np.array_equal(u, u2)
+        assert (s._graphs.captured > 0) == graphs
+        outs.append((u, info))
+    assert outs[0][1]["residual_history"] == outs[1][1]["residual_history"] and np.array_equal(outs[0][0], outs[1][0])
+    assert outs[1][1]["iterations"] == 8 and abs(outs[1][1]["final_residual"] - 1.043e-9) < 1e-11
+    # the reference's default (lexicographic) smoother is not fused: it runs eagerly, as before
+    s = MultigridSolver(max_levels=5, max_iterations=12, tolerance=1e-8)
+    s.setup(Grid(65, 65), op, RestrictionOperator(), ProlongationOperator())
+    _, info = s.solve(Grid(65, 65), op, O.mms_rhs(65))
+    assert info["iterations"] == 9 and s._graphs.captured == 0
