@@ -76,6 +76,8 @@ def parse():
                     help="1-GPU arm: the variable-coefficient operator -div(a grad u), a = 1 + 0.5 sin(2 pi x) cos(pi y) + x y "
                          "(the operator of BASELINE configs[4]) through the mg_vcv_* passes; use with --n 8193")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-dd", action="store_true", help="A/B: separate defect pass and down pass (two launches) "
+                                                         "instead of the fused defect + down pass")
     return ap.parse_args()
 
 
@@ -347,7 +349,8 @@ def gpu_arm(a):
     solver = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
                                      cycle_type=a.cycle, loader=a.loader, max_iterations=10 ** 9, device=dev,
                                      smoother="red_black_gauss_seidel" if a.varcoef else a.smoother,
-                                     use_cuda_graphs=not a.no_graphs, coefficient=coefficient)
+                                     use_cuda_graphs=not a.no_graphs, coefficient=coefficient,
+                                     use_fused_defect_down=not a.no_dd)
     solver.setup(n, n)
     eng, g = solver._engine, solver._grid
     b64 = eng.levels[0].bufs(torch.float64)
@@ -442,6 +445,8 @@ def gpu_arm(a):
             return alg_bytes(name[4:] + "/" + dt + "/" + dims) + w * pts
         if name.startswith("small"):      # whole coarse sub-cycle in shared memory: read f (+u), write u
             return 2.0 * w * pts
+        if name.startswith("dd:"):        # fused defect + down pass: the defect pass's traffic + e' and f_c out
+            return alg_bytes(name[3:].replace("+rbgs2+R", "") + "/" + dt + "/" + dims) + (4 + 1) * pts
         if "resid32" in name or "update" in name:
             b = 0.0
             if "resid32" in name:
@@ -496,7 +501,8 @@ def gpu_arm(a):
         f_host.copy_(b64.f)
         torch.cuda.synchronize()
         api = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=tol,
-                                      cycle_type=a.cycle, loader=a.loader, device=dev, use_cuda_graphs=not a.no_graphs)
+                                      cycle_type=a.cycle, loader=a.loader, device=dev, use_cuda_graphs=not a.no_graphs,
+                                      use_fused_defect_down=not a.no_dd)
         api._engine, api._shape, api._domain, api._grid, api._sumsq, api._pinned_out, api._graph_cache = (
             solver._engine, solver._shape, solver._domain, solver._grid, solver._sumsq, None, solver._graph_cache)
         prob = PoissonProblem(rhs=f_host, nx=n, ny=n)

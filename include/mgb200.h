@@ -220,6 +220,22 @@ MG_API int mg_varcoef_coarse_solve(void* u, const void* f, const void* a, int nx
                             int64_t ld_a, double hx, double hy, double shift, double omega, double tolerance,
                             int max_iterations, double* info, int dtype, void* stream);
 
+/* The defect pass and the pre-smoothing pass of the error equation in ONE pass over HBM (round 2): mg_vc_defect_pass_slab
+ * followed by mg_vc_pass_slab(MG_VC_U_ZERO | MG_VC_RESTRICT, sweeps = 2) -- the refinement loop of
+ * docs/methodology.md:337-360 around the down leg of solvers/multigrid.py:286-300:
+ *     u_out = u_in + (double) e_in                 (e_in NULL: u unchanged and not stored; MG_VC_U_ZERO: u_in == 0, not read)
+ *     r_out = (float)(f - A u_out),  sumsq_out[0] = sum of the squared fp64 residual over rows [norm_row_lo, norm_row_hi)
+ *     e_out = 2 red-black GS sweeps from zero on A e = r_out  (fp32; omega, coefficient, shift as in mg_vc_pass_slab)
+ *     coarse_out = R_fw(r_out - A e_out)
+ * The fp32 residual row is stored (the up pass needs it as its right-hand side) but consumed by the smoothing
+ * pipeline from registers: 37 instead of 41 bytes per point and one launch less.  u_out, r_out, e_out and coarse_out
+ * are bit-identical to the two separate passes.  TMA loader, red-black GS; fields 16-byte aligned. */
+MG_API int mg_vc_defect_down_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out,
+                                void* e_out, void* coarse_out, double* sumsq_out, double* workspace, int nx, int ny,
+                                int64_t ld_in, int64_t ld_out, int64_t ld_f, int64_t ld_e, int64_t ld_r, int64_t ld_eo,
+                                int64_t ld_co, double hx, double hy, double omega, double coefficient, int flags,
+                                int norm_row_lo, int norm_row_hi, double shift, void* stream);
+
 /* Fused / temporally blocked passes of the variable-coefficient operator  A u = -div(a grad u) + shift*u  (README.md:175
  * advertises the problem class, docs/methodology.md:710 the implicit heat system it serves; the reference ships no operator:
  * SURVEY 8f-1, parity unpinned).  Same pass structure, flags and slab semantics as mg_vc_pass_slab /

@@ -52,6 +52,8 @@ SIGNATURES = {
     "mg_varcoef_coarse_solve": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _d, _d, _i, _p, _i, _p],
     "mg_vcv_pass_slab": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _l, _l, _d, _d, _d, _i, _i, _i, _i, _i, _d, _p],
     "mg_vcv_defect_pass_slab": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _l, _l, _d, _d, _i, _i, _i, _d, _p],
+    "mg_vc_defect_down_pass_slab": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _l, _l, _l, _d, _d, _d, _d, _i,
+                                    _i, _i, _d, _p],
     "mg_residual_h": [_p, _p, _p, _i, _i, _l, _l, _l, _d, _d, _d, _d, _i, _i, _p],
     "mg_smooth_rbgs_h": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _d, _i, _i, _p],
     "mg_coarse_solve_lexgs_h": [_p, _p, _i, _i, _l, _l, _d, _d, _d, _d, _d, _d, _i, _p, _i, _p],

@@ -81,7 +81,8 @@ struct PassParams {
   int64_t ld_in, ld_out, ld_f, ld_ci, ld_co, ld_fi, ld_ro, ld_a;
   int u_zero;              // 1: u_in is identically zero and is not read
   int norm_row_lo, norm_row_hi;  // rows [lo, hi) entering the residual sum (a slab sums only the rows it owns)
-  int rows_per_tile;       // R (even)
+  int rows_per_tile;       // R (even); 0 on entry to the launcher = pick from the occupancy (pick_rows)
+  int tile_overlap;        // lead + tail rows a tile streams besides its own
   int nstrips;
   int store_u;             // 0: do not write u_out (pure residual passes)
 };

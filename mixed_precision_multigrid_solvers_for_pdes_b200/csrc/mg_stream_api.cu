@@ -2,15 +2,19 @@
 #include <cudaTypedefs.h>
 #include <string.h>
 #include "mg_stream_inst.cuh"
+#include "mg_stream_dd.cuh"
 
 namespace mg {
 namespace stream {
-int launch_pass_f32_tma(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f32_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f64_tma(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
-int launch_pass_f64_cpa(int, int, int, bool, int, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
-int launch_pass_f32_var(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<float>&, cudaStream_t);
-int launch_pass_f64_var(int, int, int, bool, const Maps&, const PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f32_tma(int, int, int, bool, int, const Maps&, PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f32_cpa(int, int, int, bool, int, const Maps&, PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_tma(int, int, int, bool, int, const Maps&, PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_pass_f64_cpa(int, int, int, bool, int, const Maps&, PassParams&, const StencilScalars<double>&, cudaStream_t);
+int launch_defect_down(bool, const CUtensorMap&, const CUtensorMap&, const CUtensorMap&, DDParams&,
+                       const StencilScalars<double>&, const StencilScalars<float>&, cudaStream_t);
+int defect_down_box_rows();
+int launch_pass_f32_var(int, int, int, bool, const Maps&, PassParams&, const StencilScalars<float>&, cudaStream_t);
+int launch_pass_f64_var(int, int, int, bool, const Maps&, PassParams&, const StencilScalars<double>&, cudaStream_t);
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -50,23 +54,6 @@ static inline int num_strips(int ny, int ns, int back) {
   while ((int64_t)stride * k - 4 + hi < ny - 1) ++k;
   return k + 1;
 }
-// Rows per tile.  A warp streams R + lead + tail rows sequentially, so a launch lasts about
-// waves * (R + overlap) row-steps, with waves = warps needed / warps resident.  Large grids want tall tiles
-// (overlap amortised), small grids want short ones (short critical path, all SMs busy).
-static inline int pick_rows(int nx, int nstrips, int overlap, int override_rows) {
-  if (override_rows > 0) return (override_rows + 1) & ~1;
-  const int64_t capacity = (int64_t)sm_count() * 12;  // resident warps (3 blocks of 4 warps per SM)
-  int best = 512;
-  int64_t best_cost = INT64_MAX;
-  for (int r = 512; r >= 8; r >>= 1) {
-    const int64_t warps = (int64_t)nstrips * ((nx + r - 1) / r);
-    const int64_t waves = (warps + capacity - 1) / capacity;
-    const int64_t cost = waves * (r + overlap);
-    if (cost < best_cost) { best_cost = cost; best = r; }
-  }
-  return best;
-}
-
 }  // namespace stream
 }  // namespace mg
 
@@ -139,7 +126,8 @@ static int run_pass(const void* u_in, void* u_out, const void* f, const void* co
   p.norm_row_lo = norm_lo < 0 ? 0 : norm_lo;
   p.norm_row_hi = (norm_hi < 0 || norm_hi > nx) ? nx : norm_hi;
   p.nstrips = num_strips(ny, ns, back);
-  p.rows_per_tile = pick_rows(nx, p.nstrips, 2 * halo(ns, back) + 2, rows_override);
+  p.rows_per_tile = rows_override > 0 ? ((rows_override + 1) & ~1) : 0;  // 0: the launcher picks (pick_rows)
+  p.tile_overlap = 2 * halo(ns, back) + 2;
   p.store_u = store ? 1 : 0;
 
   Maps m;
@@ -193,7 +181,7 @@ extern "C" {
 
 int mg_vc_workspace_doubles(int nx, int ny) {
   if (nx < 3 || ny < 3) return 0;
-  const int nstrips = num_strips(ny, 4, 1) + WARPS;  // widest halo => smallest stride => most strips
+  const int nstrips = num_strips(ny, 6, 1) + WARPS;  // widest halo (fused defect + down pass: 8) => most strips
   const int ntiles = (nx + 7) / 8;
   return nstrips * ntiles + 8;
 }
@@ -275,6 +263,58 @@ int mg_vcv_defect_pass_slab(const void* u_in, void* u_out, const void* f, const 
   return run_pass(u_in, e_in ? u_out : nullptr, f, nullptr, nullptr, (const float*)e_in, (float*)r_out, sumsq_out,
                   workspace, nx, ny, ld_in, ld_out, ld_f, 0, 0, ld_e, ld_r, hx, hy, 1.0, 1.0, 0, MG_F64, front, back, fl,
                   stream, "mg_vcv_defect_pass_slab", norm_row_lo, norm_row_hi, shift, a, ld_a);
+}
+
+int mg_vc_defect_down_pass_slab(const void* u_in, void* u_out, const void* f, const void* e_in, void* r_out, void* e_out,
+                                void* coarse_out, double* sumsq_out, double* workspace, int nx, int ny, int64_t ld_in,
+                                int64_t ld_out, int64_t ld_f, int64_t ld_e, int64_t ld_r, int64_t ld_eo, int64_t ld_co,
+                                double hx, double hy, double omega, double coefficient, int flags, int norm_row_lo,
+                                int norm_row_hi, double shift, void* stream) {
+  const bool u_zero = (flags & MG_VC_U_ZERO) != 0, has_e = e_in != nullptr;
+  const int rows_override = (flags >> 8) & 0xFFF;
+  if (flags & (MG_VC_JACOBI | MG_VC_LOADER_CPASYNC)) return MG_ERR_UNSUPPORTED;
+  if (!f || !r_out || !e_out || !coarse_out || !sumsq_out || !workspace || nx < 3 || ny < 3 || hx <= 0 || hy <= 0 ||
+      !(shift >= 0.0) || ld_f < ny || ld_r < ny || ld_eo < ny)
+    return MG_ERR_BADARG;
+  if ((ny - 1) % 2) return MG_ERR_BADARG;  // an even nx is a row slab whose last local row is a ghost row
+  const int nxc = (nx - 1) / 2 + 1, nyc = (ny - 1) / 2 + 1;
+  if (ld_co < nyc) return MG_ERR_BADARG;
+  if (!u_zero && (!u_in || ld_in < ny)) return MG_ERR_BADARG;
+  if (has_e && (!u_out || ld_out < ny || ld_e < ny || u_out == u_in)) return MG_ERR_BADARG;
+  if (rows_override > 0 && rows_override < 8) return MG_ERR_BADARG;
+  auto mis = [&](const void* q, int64_t ld, size_t es) { return q && (((uintptr_t)q & 15u) || (ld % (int64_t)(16 / es))); };
+  if ((!u_zero && mis(u_in, ld_in, 8)) || mis(f, ld_f, 8) || (has_e && (mis(u_out, ld_out, 8) || mis(e_in, ld_e, 4))) ||
+      mis(r_out, ld_r, 4) || mis(e_out, ld_eo, 4) || mis(coarse_out, ld_co, 4))
+    return MG_ERR_ALIGN;
+  DDParams p;
+  memset(&p, 0, sizeof(p));
+  p.u_in = (const double*)(u_zero ? f : u_in);
+  p.u_out = (double*)u_out; p.f = (const double*)f; p.e_in = (const float*)e_in;
+  p.r_out = (float*)r_out; p.e_out = (float*)e_out; p.coarse_out = (float*)coarse_out; p.partials = workspace;
+  p.nx = nx; p.ny = ny; p.nxc = nxc; p.nyc = nyc;
+  p.ld_u = u_zero ? ld_f : ld_in; p.ld_uo = ld_out; p.ld_f = ld_f; p.ld_e = ld_e; p.ld_r = ld_r; p.ld_eo = ld_eo; p.ld_co = ld_co;
+  p.u_zero = u_zero ? 1 : 0; p.has_e = has_e ? 1 : 0;
+  p.norm_row_lo = norm_row_lo < 0 ? 0 : norm_row_lo;
+  p.norm_row_hi = (norm_row_hi < 0 || norm_row_hi > nx) ? nx : norm_row_hi;
+  p.nstrips = num_strips(ny, 6, 1);  // halo 8: see DDGeometry
+  p.rows_per_tile = rows_override > 0 ? ((rows_override + 1) & ~1) : 0;  // 0: the launcher picks (pick_rows)
+  CUtensorMap mu, mf, me;
+  memset(&mu, 0, sizeof(mu)); memset(&me, 0, sizeof(me));
+  int rc = MG_OK;
+  const int box_rows = defect_down_box_rows();
+  if (!u_zero) rc = make_map(&mu, u_in, nx, ny, ld_in, MG_F64, STRIP, box_rows);
+  if (rc == MG_OK) rc = make_map(&mf, f, nx, ny, ld_f, MG_F64, STRIP, box_rows);
+  if (rc == MG_OK && has_e) rc = make_map(&me, e_in, nx, ny, ld_e, MG_F32, STRIP, box_rows);
+  if (rc != MG_OK) return rc;
+  cudaStream_t st = as_stream(stream);
+  const bool simple = (omega == 1.0) && (hx == hy);
+  auto sd = make_scalars<double>(hx, hy, omega, coefficient, shift);
+  auto sf = make_scalars<float>(hx, hy, omega, coefficient, shift);
+  rc = launch_defect_down(simple, mu, mf, me, p, sd, sf, st);
+  if (rc != MG_OK) return rc;
+  const int ntiles = (nx + p.rows_per_tile - 1) / p.rows_per_tile;
+  reduce_partials_sum(workspace, ((p.nstrips + WARPS - 1) / WARPS) * WARPS * ntiles, sumsq_out, st);
+  return check_launch("mg_vc_defect_down_pass_slab", 2);
 }
 
 int mg_vc_smooth(const void* u_in, void* u_out, const void* f, int nx, int ny, int64_t ld_in, int64_t ld_out,

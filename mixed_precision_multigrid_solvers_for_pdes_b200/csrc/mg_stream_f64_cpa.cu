@@ -1,7 +1,7 @@
 // Instantiations of the streaming kernel for T = double, loader = LOADER_CPASYNC.
 #include "mg_stream_inst.cuh"
 namespace mg { namespace stream {
-int launch_pass_f64_cpa(int nu, int front, int back, bool simple, int smooth, const Maps& m, const PassParams& p,
+int launch_pass_f64_cpa(int nu, int front, int back, bool simple, int smooth, const Maps& m, PassParams& p,
                        const StencilScalars<double>& sc, cudaStream_t st) {
   return launch_pass<double, LOADER_CPASYNC>(nu, front, back, simple, smooth, m, p, sc, st);
 }

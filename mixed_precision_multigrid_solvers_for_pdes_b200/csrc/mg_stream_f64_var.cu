@@ -1,7 +1,7 @@
 // Instantiations of the streaming kernel for T = double with variable coefficients (TMA loader).
 #include "mg_stream_inst.cuh"
 namespace mg { namespace stream {
-int launch_pass_f64_var(int nu, int front, int back, bool noblend, const Maps& m, const PassParams& p,
+int launch_pass_f64_var(int nu, int front, int back, bool noblend, const Maps& m, PassParams& p,
                        const StencilScalars<double>& sc, cudaStream_t st) {
   return launch_pass_var<double>(nu, front, back, noblend, m, p, sc, st);
 }

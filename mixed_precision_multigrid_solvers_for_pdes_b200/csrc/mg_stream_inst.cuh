@@ -13,12 +13,31 @@ constexpr int RB = 4;
 template <typename T> struct Stages { static constexpr int N = 3; };
 template <> struct Stages<double> { static constexpr int N = 2; };
 
+// Rows per tile.  A warp streams R + lead + tail rows sequentially, so a launch lasts about
+// waves * (R + overlap) row-steps, with waves = warps needed / warps resident.  Large grids want tall tiles
+// (overlap amortised), small grids want short ones (short critical path, all SMs busy) -- but never taller than
+// 128 rows: measured on 16385^2 (tools/bench_dd.py, profiles/r02_dd_tile_sweep.log) every pass slows down beyond
+// that (256 rows: +3..12 %, 512 rows: +7..33 %; tiles that fill whole waves exactly, e.g. 514 rows, too), because
+// short tiles keep the rows that are streamed concurrently close together in memory and the halo rows in L2.
+static inline int pick_rows(int nx, int nstrips, int overlap) {
+  const int64_t capacity = (int64_t)sm_count() * 12;  // resident warps (3 blocks of 4 warps per SM)
+  int best = 128;
+  int64_t best_cost = INT64_MAX;
+  for (int r = 128; r >= 8; r >>= 1) {
+    const int64_t warps = (int64_t)nstrips * ((nx + r - 1) / r);
+    const int64_t waves = (warps + capacity - 1) / capacity;
+    const int64_t cost = waves * (r + overlap);
+    if (cost < best_cost) { best_cost = cost; best = r; }
+  }
+  return best;
+}
+
 struct Maps {
   CUtensorMap u, f, e, a;
 };
 
 template <typename T, int NU, int FRONT, int BACK, int LOADER, bool SIMPLE, int SMOOTH = SMOOTH_RBGS, bool VARCOEF = false>
-static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
+static int launch_one(const Maps& m, PassParams& p, const StencilScalars<T>& sc, cudaStream_t st) {
   // fp32 prolongation passes carry the coarse slab in every stage: 2 stages keep 5 blocks (20 warps) per SM
   constexpr int NS = ((sizeof(T) == 4 && FRONT == FRONT_PROLONG && LOADER == LOADER_TMA) || VARCOEF) ? 2 : Stages<T>::N;
   auto kern = rbgs_stream_kernel<T, NU, FRONT, BACK, LOADER, SIMPLE, SMOOTH, WARPS, NS, RB, VARCOEF>;
@@ -34,6 +53,7 @@ static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured[dev] = true;
   }
+  if (p.rows_per_tile <= 0) p.rows_per_tile = pick_rows(p.nx, p.nstrips, p.tile_overlap);
   const int ntiles = (p.nx + p.rows_per_tile - 1) / p.rows_per_tile;
   dim3 grid((p.nstrips + WARPS - 1) / WARPS, ntiles);
   kern<<<grid, WARPS * 32, smem, st>>>(m.u, m.f, m.e, m.a, p, sc);
@@ -43,7 +63,7 @@ static int launch_one(const Maps& m, const PassParams& p, const StencilScalars<T
 // smooth: SMOOTH_RBGS or SMOOTH_JACOBI (damped Jacobi sweeps; TMA loader only, and always the general point
 // update: omega = 1 Jacobi is not a smoother, so it gets no specialised instantiation)
 template <typename T, int LOADER>
-int launch_pass(int nu, int front, int back, bool simple, int smooth, const Maps& m, const PassParams& p,
+int launch_pass(int nu, int front, int back, bool simple, int smooth, const Maps& m, PassParams& p,
                 const StencilScalars<T>& sc, cudaStream_t st) {
   if (smooth == SMOOTH_JACOBI && nu > 0) {
     if constexpr (LOADER == LOADER_TMA) {
@@ -78,7 +98,7 @@ int launch_pass(int nu, int front, int back, bool simple, int smooth, const Maps
 // fp64 keeps to one sweep per pass: a 2-sweep fp64 pass would hold 188 registers of row windows (u, f and the
 // coefficient rows with their shuffled neighbour columns) before any temporaries.
 template <typename T>
-int launch_pass_var(int nu, int front, int back, bool noblend, const Maps& m, const PassParams& p,
+int launch_pass_var(int nu, int front, int back, bool noblend, const Maps& m, PassParams& p,
                     const StencilScalars<T>& sc, cudaStream_t st) {
 #define MG_VCASE(NU_, FR_, BK_)                                                                              \
   if (nu == NU_ && front == FR_ && back == BK_)                                                              \

@@ -427,6 +427,42 @@ def vc_defect_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.T
                               + ("resid32+N" if r_out is not None else "") + f"/f64/{nx}x{ny}", ev0, ev1))
 
 
+def vc_defect_down_pass(u_in: torch.Tensor, u_out: Optional[torch.Tensor], f: torch.Tensor, hx: float, hy: float, *,
+                        e_in: Optional[torch.Tensor], r_out: torch.Tensor, e_out: torch.Tensor, coarse_out: torch.Tensor,
+                        sumsq_out: torch.Tensor, omega: float = 1.0, coefficient: float = -1.0, shift: float = 0.0,
+                        u_zero: bool = False, norm_rows: Optional[Tuple[int, int]] = None, rows: int = 0,
+                        workspace: Optional[torch.Tensor] = None) -> None:
+    """Defect pass + pre-smoothing pass of the error equation in one HBM pass (mg_vc_defect_down_pass_slab):
+    u_out = u_in + e_in (e_in None: u unchanged, nothing stored); r_out = fp32(f - A u_out); sumsq_out[0] = sum r^2 (fp64);
+    e_out = 2 RB-GS sweeps from zero on A e = r_out; coarse_out = R(r_out - A e_out).  Bit-identical to vc_defect_pass
+    followed by vc_pass(u_zero=True, sweeps=2, coarse_out=...)."""
+    nx, ny = f.shape
+    if f.dtype != torch.float64 or (not u_zero and u_in.dtype != torch.float64):
+        raise TypeError("vc_defect_down_pass: the iterate and right-hand side are fp64")
+    for t in (e_in, r_out, e_out, coarse_out):
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError("vc_defect_down_pass: correction, residual, error iterate and coarse right-hand side are fp32")
+    flags = ((rows & 0xFFF) << 8) | (_lib.VC_U_ZERO if u_zero else 0)
+    ws = workspace if workspace is not None else _vc_workspace(f.device, nx, ny)
+    if ws.numel() < vc_workspace_doubles(nx, ny):
+        raise ValueError("vc_defect_down_pass: workspace too small for this grid (see vc_workspace_doubles)")
+    timed = TIMER is not None and nx * ny >= TIMER.min_points
+    if timed:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    nlo, nhi = norm_rows if norm_rows is not None else (0, -1)
+    _lib.call("mg_vc_defect_down_pass_slab", None if u_zero else u_in.data_ptr(),
+              u_out.data_ptr() if (u_out is not None and e_in is not None) else None, f.data_ptr(),
+              e_in.data_ptr() if e_in is not None else None, r_out.data_ptr(), e_out.data_ptr(), coarse_out.data_ptr(),
+              sumsq_out.data_ptr(), ws.data_ptr(), nx, ny, 0 if u_zero else ld(u_in),
+              ld(u_out) if (u_out is not None and e_in is not None) else 0, ld(f), ld(e_in) if e_in is not None else 0,
+              ld(r_out), ld(e_out), ld(coarse_out), hx, hy, omega, coefficient, flags, nlo, nhi, shift, stream_ptr())
+    if timed:
+        ev1.record()
+        TIMER.records.append(("dd:" + ("Z+" if u_zero else "") + ("update+" if e_in is not None else "")
+                              + f"resid32+N+rbgs2+R/f64/{nx}x{ny}", ev0, ev1))
+
+
 def varcoef_coarse_solve_(u: torch.Tensor, f: torch.Tensor, a: torch.Tensor, hx: float, hy: float, shift: float = 0.0,
                           omega: float = 1.0, tolerance: float = 1e-12, max_iterations: int = 1000,
                           info: Optional[torch.Tensor] = None) -> torch.Tensor:

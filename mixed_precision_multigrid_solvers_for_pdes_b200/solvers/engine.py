@@ -194,7 +194,7 @@ class CycleEngine:
             return max(1, 2 ** (L - lvl - 2))
         return 0  # reference: unknown cycle strings fall through all branches (multigrid.py:309-319)
 
-    def _cycle_fused(self, level_dtypes, lvl, precision_manager, sumsq_out, u_zero) -> None:
+    def _cycle_fused(self, level_dtypes, lvl, precision_manager, sumsq_out, u_zero, skip_down: bool = False) -> None:
         g = self.levels[lvl].grid
         b = self.levels[lvl].bufs(level_dtypes[lvl])
         c = self.levels[lvl + 1].bufs(level_dtypes[lvl + 1])
@@ -211,8 +211,12 @@ class CycleEngine:
             kw["coefficient"] = op.coefficient
             kw["smoother"] = self.smoother.kind  # "rbgs" or "jacobi": same passes, the sweeps differ
         # down: pre-smooth (`ms` sweeps per HBM pass) with residual + restriction fused into the last pass
-        n = self.pre
-        if u_zero and n == 0:
+        # (skip_down: the caller's fused defect + down pass has already left the pre-smoothed iterate in b.u and the
+        # restricted residual in c.f, ops.vc_defect_down_pass)
+        n = 0 if skip_down else self.pre
+        if skip_down:
+            pass
+        elif u_zero and n == 0:
             ops.zero_(b.u)  # nothing will overwrite the iterate before it is read
             u_zero = False
         while n > ms:
@@ -223,7 +227,7 @@ class CycleEngine:
         if n > 0:
             ops.vc_pass(b.u, b.tmp, b.f, g.hx, g.hy, sweeps=n, coarse_out=c.f, u_zero=u_zero, **kw)
             b.u, b.tmp = b.tmp, b.u
-        else:
+        elif not skip_down:
             ops.vc_pass(b.u, None, b.f, g.hx, g.hy, sweeps=0, coarse_out=c.f, **kw)
         # the coarse error equation starts from e = 0: the first coarse pass is told so instead of reading zeros
         for rep in range(self._reps(lvl)):
@@ -245,13 +249,18 @@ class CycleEngine:
 
     # -- the recursion ------------------------------------------------------------------------------
     def cycle(self, level_dtypes: Sequence, lvl: int = 0, precision_manager=None, sumsq_out=None,
-              u_zero: bool = False) -> bool:
+              u_zero: bool = False, skip_down: bool = False) -> bool:
         """One cycle on level `lvl`, updating that level's ``u`` for ``level_dtypes[lvl]``.
         With ``sumsq_out`` (1 float64 on the device) the fused path also leaves sum((f - A u)^2) of the
         final iterate there; returns True when it did.  ``u_zero``: the iterate of this level is to be
         taken as zero whatever its buffer holds (the zero initial guess of a coarse error equation)."""
         L = self.num_levels
         b = self.levels[lvl].bufs(level_dtypes[lvl])
+        if skip_down:  # only the fused path can pick a cycle up after its down pass
+            if not (lvl < L - 1 and self._fusable(lvl, level_dtypes)) or self._small_ok(lvl, level_dtypes):
+                raise ValueError("skip_down needs a fused level")
+            self._cycle_fused(level_dtypes, lvl, precision_manager, sumsq_out, u_zero, skip_down=True)
+            return sumsq_out is not None
         if precision_manager is None and self._small_ok(lvl, level_dtypes):
             self._small_cycle(lvl, level_dtypes, u_zero)
             return False

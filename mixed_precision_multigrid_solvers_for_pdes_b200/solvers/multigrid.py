@@ -184,7 +184,9 @@ class MultigridSolver(BaseSolver):
             except ValueError:
                 ok = False
                 break
-        self._graphable_cache = dict(getattr(self, "_graphable_cache", {}), **{key: ok})
+        cache = dict(getattr(self, "_graphable_cache", {}))
+        cache[key] = ok
+        self._graphable_cache = cache
         return ok
 
     def apply_cycles(self, rhs, num_cycles: int = 1, initial_guess=None):

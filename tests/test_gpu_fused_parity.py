@@ -174,7 +174,7 @@ def test_jacobi_large_grid_against_basic_kernels():
         u, f = empty_field(n, n, dt), empty_field(n, n, dt)
         u.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
         f.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
-        ref = u.clone()
+        ref = u.copy()
         ops.smooth_jacobi_(ref, f, g.hx, g.hy, 2.0 / 3.0, 2)
         rref = ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0))
         for rows in (0, 64):
@@ -262,7 +262,7 @@ def test_large_grid_against_basic_kernels():
         out = empty_field(n, n, dt)
         rc = empty_field(2049, 2049, dt)
         ops.vc_pass(u, out, f, g.hx, g.hy, sweeps=2, coarse_out=rc)
-        ref = u.clone()
+        ref = u.copy()
         ops.smooth_rbgs_(ref, f, g.hx, g.hy, 1.0, 2)
         assert torch.equal(out, ref)
         assert torch.equal(rc, ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0)))
@@ -314,3 +314,64 @@ def test_defect_pass(n, m, loader):
     uo2 = empty_field(n, m, np.float64)
     ops.vc_defect_pass(du, uo2, df, g.hx, g.hy, e_in=de, loader=loader)
     assert torch.equal(uo2, uo)
+
+
+@pytest.mark.parametrize("shift", [0.0, 37.5])
+@pytest.mark.parametrize("n,m", [(129, 129), (257, 65), (33, 1025), (9, 9), (17, 33), (513, 513), (1025, 257), (449, 129)])
+def test_defect_down_pass(n, m, shift):
+    """ONE pass (mg_stream_dd.cuh) = the defect pass followed by the first pass of the fp32 error cycle, bit for bit:
+    u += e ; r32 ; ||r|| ; e' = 2 RB-GS sweeps from zero on A e = r32 ; f_c = R(r32 - A e')."""
+    rng = np.random.default_rng(17)
+    g = Grid(n, m)
+    u, f = rng.uniform(-1, 1, (n, m)), rng.uniform(-1, 1, (n, m)) * 1e3
+    e = rng.uniform(-1, 1, (n, m)).astype(np.float32)
+    for a in (u, f, e):  # homogeneous Dirichlet ring, as in the solver
+        a[0, :] = a[-1, :] = 0
+        a[:, 0] = a[:, -1] = 0
+    du, df, de = to_device(u)[0], to_device(f)[0], to_device(e)[0]
+    nc, mc = (n + 1) // 2, (m + 1) // 2
+    for with_e in (True, False):
+        for u_zero in (False, True):
+            if with_e and u_zero:
+                uin = torch.full_like(du, float("nan"))  # U_ZERO: never read
+            else:
+                uin = du
+            # two-launch reference
+            uo = empty_field(n, m, np.float64)
+            r32, eo, tmp = (empty_field(n, m, np.float32) for _ in range(3))
+            co = empty_field(nc, mc, np.float32)
+            ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+            ops.vc_defect_pass(uin, uo if with_e else None, df, g.hx, g.hy, e_in=de if with_e else None, r_out=r32,
+                               sumsq_out=ss, shift=shift, u_zero=u_zero)
+            ops.vc_pass(tmp, eo, r32, g.hx, g.hy, sweeps=2, coarse_out=co, u_zero=True, shift=shift)
+            # fused
+            uo2 = empty_field(n, m, np.float64)
+            r32b, eo2 = empty_field(n, m, np.float32), empty_field(n, m, np.float32)
+            co2 = empty_field(nc, mc, np.float32)
+            ss2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+            ops.vc_defect_down_pass(uin, uo2 if with_e else None, df, g.hx, g.hy, e_in=de if with_e else None,
+                                    r_out=r32b, e_out=eo2, coarse_out=co2, sumsq_out=ss2, shift=shift, u_zero=u_zero)
+            what = f"{n}x{m} e={with_e} u_zero={u_zero} shift={shift}"
+            if with_e:
+                assert torch.equal(uo2, uo), "iterate " + what
+            _cmp(r32b, to_host(r32), True, "residual " + what)
+            _cmp(eo2[1:-1, 1:-1], to_host(eo)[1:-1, 1:-1], True, "pre-smoothed error " + what)
+            _cmp(co2[1:-1, 1:-1], to_host(co)[1:-1, 1:-1], True, "restricted residual " + what)
+            assert abs(ss2.item() - ss.item()) <= 1e-12 * ss.item(), "norm " + what
+            assert torch.count_nonzero(eo2[0]) == 0 and torch.count_nonzero(eo2[:, 0]) == 0 and \
+                torch.count_nonzero(eo2[-1]) == 0 and torch.count_nonzero(eo2[:, -1]) == 0, "ring " + what
+
+
+def test_defect_down_refinement_matches_two_pass_refinement():
+    """The solver with the fused defect + down pass walks through the SAME residual history as with two launches."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MixedPrecisionMultigrid, PoissonProblem
+    hist = []
+    for dd in (True, False):
+        s = MixedPrecisionMultigrid(tolerance=1e-9, use_fused_defect_down=dd)
+        u, info = s.solve(PoissonProblem.manufactured(1025))
+        assert s._dd_ok() == dd
+        hist.append((info["residual_history"], u.copy()))
+    # the two kernels sum the squared residual over different strip widths: same norm up to summation order
+    assert len(hist[0][0]) >= 8 and len(hist[0][0]) == len(hist[1][0])
+    np.testing.assert_allclose(hist[0][0], hist[1][0], rtol=1e-12)
+    assert np.array_equal(hist[0][1], hist[1][1])
