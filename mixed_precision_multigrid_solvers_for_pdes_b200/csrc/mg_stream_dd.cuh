@@ -29,7 +29,12 @@ struct DDGeometry {
   static constexpr int NS = 4;          // two red-black sweeps = four half-sweep stages
   static constexpr int H = 8;           // halo rows / columns
   static constexpr int OWN_LO = 8, OWN_HI = STRIP - 1 - OWN_LO, STRIDE = OWN_HI - OWN_LO + 1;  // 112 owned columns
-  static constexpr int ROW_LEAD = H, ROW_TAIL = H;
+  // Rows a tile streams besides its own [I0, I1).  Dependence cone: the restricted residual centred on row I0 reads
+  // residual rows >= I0-1, those read e' rows >= I0-2, four half-sweeps from a ZERO iterate reach three rows further
+  // into the right-hand side (r32 rows >= I0-5), and r32(I0-5) reads u row I0-6.  Downwards the loop emits the
+  // restriction centred on row i-7 when it loads row i: centres <= I1-2 in tiles that end on an even row (all but
+  // the last, which ends at the odd nx and needs one row more; rows >= nx are never loaded anyway).
+  static constexpr int ROW_LEAD = 6, ROW_TAIL = 6, ROW_TAIL_LAST = 8;
   static constexpr int WR = NS + 3;     // e' window: ages 0 .. NS+2 (residual stage reads ages NS .. NS+2)
   static constexpr int FR = NS + 2;     // r32 window: ages 0 .. NS+1
 };
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   const int I0 = blockIdx.y * p.rows_per_tile;
   const int I1 = min(I0 + p.rows_per_tile, nx);
   const int i_begin = I0 - G::ROW_LEAD;  // even
-  const int i_last = I1 - 1 + G::ROW_TAIL;
+  const int i_last = I1 - 1 + ((I1 & 1) ? G::ROW_TAIL_LAST : G::ROW_TAIL);
   const int nbox = (i_last - i_begin + 1 + RB - 1) / RB;
   const bool u_zero = p.u_zero != 0, has_e = p.has_e != 0;
   const bool strip_interior = (g0 >= 1) && (g0 + STRIP - 1 <= ny - 2);

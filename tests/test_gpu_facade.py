@@ -245,5 +245,5 @@ def test_level_timings_are_filled_by_profile_levels():
     lt = s.profile_levels(cycles=2)
     _, info = s.solve(p)
     assert info["level_timings"] == lt and set(lt) == set(range(info["num_levels"]))
-    assert lt[0]["smooth_time"] > 0 and lt[0]["passes"] >= 3 and lt[1]["smooth_time"] > 0
+    assert lt[0]["smooth_time"] > 0 and lt[0]["passes"] >= 2 and lt[1]["smooth_time"] > 0
     assert lt[0]["smooth_time"] > lt[2]["smooth_time"]

@@ -174,7 +174,7 @@ def test_jacobi_large_grid_against_basic_kernels():
         u, f = empty_field(n, n, dt), empty_field(n, n, dt)
         u.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
         f.copy_(torch.rand((n, n), generator=gen, device="cuda", dtype=dt) * 2 - 1)
-        ref = u.copy()
+        ref = u.clone()
         ops.smooth_jacobi_(ref, f, g.hx, g.hy, 2.0 / 3.0, 2)
         rref = ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0))
         for rows in (0, 64):
@@ -262,7 +262,7 @@ def test_large_grid_against_basic_kernels():
         out = empty_field(n, n, dt)
         rc = empty_field(2049, 2049, dt)
         ops.vc_pass(u, out, f, g.hx, g.hy, sweeps=2, coarse_out=rc)
-        ref = u.copy()
+        ref = u.clone()
         ops.smooth_rbgs_(ref, f, g.hx, g.hy, 1.0, 2)
         assert torch.equal(out, ref)
         assert torch.equal(rc, ops.restrict(ops.residual(ref, f, g.hx, g.hy, -1.0)))
@@ -349,17 +349,21 @@ def test_defect_down_pass(n, m, shift):
             r32b, eo2 = empty_field(n, m, np.float32), empty_field(n, m, np.float32)
             co2 = empty_field(nc, mc, np.float32)
             ss2 = torch.zeros(1, dtype=torch.float64, device="cuda")
-            ops.vc_defect_down_pass(uin, uo2 if with_e else None, df, g.hx, g.hy, e_in=de if with_e else None,
-                                    r_out=r32b, e_out=eo2, coarse_out=co2, sumsq_out=ss2, shift=shift, u_zero=u_zero)
-            what = f"{n}x{m} e={with_e} u_zero={u_zero} shift={shift}"
-            if with_e:
-                assert torch.equal(uo2, uo), "iterate " + what
-            _cmp(r32b, to_host(r32), True, "residual " + what)
-            _cmp(eo2[1:-1, 1:-1], to_host(eo)[1:-1, 1:-1], True, "pre-smoothed error " + what)
-            _cmp(co2[1:-1, 1:-1], to_host(co)[1:-1, 1:-1], True, "restricted residual " + what)
-            assert abs(ss2.item() - ss.item()) <= 1e-12 * ss.item(), "norm " + what
-            assert torch.count_nonzero(eo2[0]) == 0 and torch.count_nonzero(eo2[:, 0]) == 0 and \
-                torch.count_nonzero(eo2[-1]) == 0 and torch.count_nonzero(eo2[:, -1]) == 0, "ring " + what
+            for rows in (0, 8, 22, 40):  # tile heights: the row halo must cover the dependence cone exactly
+                for t in (uo2, r32b, eo2, co2):
+                    t.fill_(float("nan"))
+                ops.vc_defect_down_pass(uin, uo2 if with_e else None, df, g.hx, g.hy, e_in=de if with_e else None,
+                                        r_out=r32b, e_out=eo2, coarse_out=co2, sumsq_out=ss2, shift=shift,
+                                        u_zero=u_zero, rows=rows)
+                what = f"{n}x{m} e={with_e} u_zero={u_zero} shift={shift} rows={rows}"
+                if with_e:
+                    assert torch.equal(uo2, uo), "iterate " + what
+                _cmp(r32b, to_host(r32), True, "residual " + what)
+                _cmp(eo2[1:-1, 1:-1], to_host(eo)[1:-1, 1:-1], True, "pre-smoothed error " + what)
+                _cmp(co2[1:-1, 1:-1], to_host(co)[1:-1, 1:-1], True, "restricted residual " + what)
+                assert abs(ss2.item() - ss.item()) <= 1e-12 * ss.item(), "norm " + what
+                assert torch.count_nonzero(eo2[0]) == 0 and torch.count_nonzero(eo2[:, 0]) == 0 and \
+                    torch.count_nonzero(eo2[-1]) == 0 and torch.count_nonzero(eo2[:, -1]) == 0, "ring " + what
 
 
 def test_defect_down_refinement_matches_two_pass_refinement():

@@ -52,9 +52,12 @@ for rows in ROWS:
     def down():
         ops.vc_pass(tmp, eo, r, h, h, sweeps=2, coarse_out=co, u_zero=True, rows=rows)
 
+    def up():
+        ops.vc_pass(eo, tmp, r, h, h, sweeps=2, coarse_in=co)
+
     out = {"n": n, "rows": rows, "variant": os.environ.get("MG_DD_VARIANT", "0"), "fused_ms": timed(fused)}
     if os.environ.get("MG_DD_VARIANT", "0") == "0":
-        out["defect_ms"], out["down_ms"] = timed(defect), timed(down)
+        out["defect_ms"], out["down_ms"], out["up_ms"] = timed(defect), timed(down), timed(up)
         out["two_launch_ms"] = out["defect_ms"] + out["down_ms"]
     out["fused_gbs"] = 37.0 * pts / out["fused_ms"] / 1e6
     print(json.dumps({k: round(v, 4) if isinstance(v, float) else v for k, v in out.items()}), flush=True)
