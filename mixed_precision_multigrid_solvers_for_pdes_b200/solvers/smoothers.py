@@ -48,9 +48,11 @@ class WeightedJacobiSmoother(JacobiSmoother):
 class GaussSeidelSmoother(_DeviceSmoother):
     """solvers/smoothers.py:89-207.  ``red_black=True`` is the smoother this build is about (fused, temporally blocked,
     HBM-bound).  ``red_black=False`` -- the reference's default, and what `MultigridSolver.setup(smoother=None)` picks
-    (multigrid.py:112-117) -- is the lexicographic sweep: a chain of nx + ny - 3 dependent wavefronts walked by ONE
-    thread block (`mg_smooth_lexgs`), bit-exact but ~0.6 ms per sweep at 1025^2 on one SM.  Use it for parity runs and
-    as the coarsest-level solver; pass a red-black smoother for anything large."""
+    (multigrid.py:112-117) -- is the lexicographic sweep, run as a skewed wavefront pipelined over all warps of the grid
+    (`mg_smooth_lexgs` -> lexgs_pipe_kernel: one warp per 32 rows, each row one step behind the row above): bit-exact
+    with the sequential loop at any size.  A sweep is still a dependency chain of about ny + 2 * nx steps (0.6 ms at
+    1025^2, 12 ms at 16385^2; a red-black sweep of 16385^2 takes 0.25 ms), so pass a red-black smoother whenever the
+    ordering is free."""
 
     def __init__(self, max_iterations: int = 1000, tolerance: float = 1e-8, relaxation_parameter: float = 1.0,
                  verbose: bool = False, red_black: bool = False):

@@ -97,6 +97,28 @@ def test_ops_match_oracle_on_fresh_inputs(n, m, dt):
         _eq(ProlongationOperator().apply(cg, uc, g), O.prolong(uc), "prolong")
 
 
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,m", [(1025, 513), (259, 1031), (2049, 2049), (35, 130), (66, 4), (3, 3), (34, 9)])
+def test_lexicographic_gs_pipelined_over_warps_is_the_sequential_sweep(n, m, dt):
+    """mg_smooth_lexgs runs the sweep as a skewed wavefront over many warps / CTAs (lexgs_pipe_kernel); the result is
+    the sequential loop's (C oracle, smoothers.py:153-173) bit for bit: forward, backward and symmetric, any size."""
+    from oracle import c_oracle as CO
+    rng = np.random.default_rng(n + m)
+    g = Grid(n, m, (0.0, 1.0, 0.0, 2.0), dt)
+    u = rng.uniform(-1, 1, (n, m)).astype(dt)
+    f = rng.uniform(-1, 1, (n, m)).astype(dt)
+    fwd = CO.lexgs_smooth(u, f, g.hx, g.hy, 0.9, 2)
+    du, df = to_device(u)[0], to_device(f)[0]
+    _eq(to_host(ops.smooth_lexgs_(du, df, g.hx, g.hy, 0.9, 2, "forward")), fwd, "forward")
+    flip = lambda a: np.ascontiguousarray(a[::-1, ::-1])  # noqa: E731
+    bwd = flip(CO.lexgs_smooth(flip(u), flip(f), g.hx, g.hy, 0.9, 1))
+    du = to_device(u)[0]
+    _eq(to_host(ops.smooth_lexgs_(du, df, g.hx, g.hy, 0.9, 1, "backward")), bwd, "backward")
+    sym = flip(CO.lexgs_smooth(flip(CO.lexgs_smooth(u, f, g.hx, g.hy, 0.9, 1)), flip(f), g.hx, g.hy, 0.9, 1))
+    du = to_device(u)[0]
+    _eq(to_host(ops.smooth_lexgs_(du, df, g.hx, g.hy, 0.9, 1, "symmetric")), sym, "symmetric")
+
+
 def test_symmetric_gs_is_forward_then_backward():
     rng = np.random.default_rng(7)
     g = Grid(17, 33)
