@@ -988,8 +988,8 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
         name, dtn, _ = tag.split("/")
         w = 8 if dtn == "f64" else 4
-        if "resid32" in name or name.startswith("update"):
-            b = (20 if "resid32" in name else 0) + (12 if name.startswith("update") else 0)
+        if "resid32" in name or "update" in name:  # defect pass: read u64, f64, write r32 (+ read e32, write u64)
+            b = (20 if "resid32" in name else 0) + (12 if "update" in name else 0) - (8 if name.startswith("Z+") else 0)
         else:
             b = 3.0 * w - (w if name.startswith("Z+") else 0) + (0.25 * w if "P+" in name else 0) + (0.25 * w if "+R" in name else 0)
         ach = b * pts / (d["mean_ms"] * 1e-3) / 1e9
