@@ -362,6 +362,33 @@ MG_API int mg_small_cycle(void* u, const void* f, int nx, int ny, int64_t ld_u, 
                    double coarse_tolerance, int coarse_max_iterations, int u_zero, double* info, int dtype,
                    int coarse_dtype, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * The reference's SECONDARY solver, CorrectedMultigridSolver (solvers/corrected_multigrid.py:24-418; the V-cycle of
+ * validation/simple_validation.py, mms_validation.py and the tutorials).  fp64, square spacing h, homogeneous
+ * Dirichlet ring; every kernel keeps the reference's operand order without fused multiply-add, so a solve reproduces
+ * the reference's solution bit for bit (tests/test_gpu_corrected.py against tests/golden/corrected_golden.npz).
+ *   mg_cm_gs           `sweeps` lexicographic GS sweeps u[i,j] = 0.25*(u[i-1,j] + u[i+1,j] + u[i,j-1] + u[i,j+1]
+ *                      + h^2 f[i,j]) in place (_gauss_seidel_iteration, :248-277), pipelined over warps like
+ *                      mg_smooth_lexgs; the ring is not touched
+ *   mg_cm_residual     r = f - (-lap_h u) inside, 0 on the ring (_compute_residual, :279-308); r may be NULL;
+ *                      sumsq_out[0] = sum r^2 = the square of _compute_residual_norm (:310-316) when given together
+ *                      with `workspace` (device, mg_cm_workspace_doubles() doubles)
+ *   mg_cm_diff_sumsq   sumsq_out[0] = sum (a - b)^2  (the ||u - u_old|| test of _solve_coarsest, :384-387)
+ *   mg_cm_restrict     full weighting / 16 on interior coarse points, 0 on the coarse ring (_restrict, :318-335)
+ *   mg_cm_prolong_add  u += P(coarse) with the textbook bilinear prolongation (_prolongate, :337-364), then the ring of
+ *                      u zeroed (_apply_boundary_conditions, :392-397) */
+MG_API int mg_cm_workspace_doubles(void);
+MG_API int mg_cm_gs(double* u, const double* f, int nx, int ny, int64_t ld_u, int64_t ld_f, double h, int sweeps,
+                    void* stream);
+MG_API int mg_cm_residual(const double* u, const double* f, double* r, double* sumsq_out, double* workspace, int nx,
+                          int ny, int64_t ld_u, int64_t ld_f, int64_t ld_r, double h, void* stream);
+MG_API int mg_cm_diff_sumsq(const double* a, const double* b, double* sumsq_out, double* workspace, int nx, int ny,
+                            int64_t ld_a, int64_t ld_b, void* stream);
+MG_API int mg_cm_restrict(const double* fine, double* coarse, int nxf, int nyf, int nxc, int nyc, int64_t ld_f,
+                          int64_t ld_c, void* stream);
+MG_API int mg_cm_prolong_add(const double* coarse, double* u, int nxc, int nyc, int nxf, int nyf, int64_t ld_c,
+                             int64_t ld_u, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ from .operators import (BaseOperator, HelmholtzOperator, LaplacianOperator, Prol
                         RestrictionOperator, VariableCoefficientOperator, VariableCoefficientSmoother)
 from .problems import (HeatProblem, HeatTestProblems, PoissonProblem, PoissonTestProblems, TimeSteppingConfig,
                        TimeSteppingMethod)
-from .solvers import (AdaptivePrecisionSolver, MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
+from .solvers import (AdaptivePrecisionSolver, CorrectedMultigridSolver, MixedPrecisionMultigrid, MixedPrecisionMultigridSolver, BaseSolver, ConvergenceHistory, GaussSeidelSmoother, IterativeSolver, JacobiSmoother,
                       MultigridCycle, MultigridSolver, SymmetricGaussSeidelSmoother, WeightedJacobiSmoother)
 
 __version__ = "0.1.0"
@@ -22,6 +22,6 @@ GPU_AVAILABLE = True  # the only path there is
 __all__ = ["Grid", "PrecisionManager", "PrecisionLevel", "BaseOperator", "LaplacianOperator", "HelmholtzOperator", "VariableCoefficientOperator", "VariableCoefficientSmoother", "HeatSolver2D", "PoissonSolver2D", "MultigridPreconditioner", "RestrictionOperator",
            "ProlongationOperator", "BaseSolver", "IterativeSolver", "ConvergenceHistory", "MultigridSolver",
            "MultigridCycle", "JacobiSmoother", "GaussSeidelSmoother", "WeightedJacobiSmoother",
-           "SymmetricGaussSeidelSmoother", "AdaptivePrecisionSolver", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",
+           "SymmetricGaussSeidelSmoother", "AdaptivePrecisionSolver", "CorrectedMultigridSolver", "MixedPrecisionMultigrid", "MixedPrecisionMultigridSolver",
            "PoissonProblem", "HeatProblem", "TimeSteppingConfig", "TimeSteppingMethod", "PoissonTestProblems",
            "HeatTestProblems", "MGLibraryError", "ops", "LIB_PATH"]

@@ -39,6 +39,12 @@ SIGNATURES = {
     "mg_axpy": [_d, _p, _p, _i, _i, _l, _l, _i, _i, _p],
     "mg_zero": [_p, _i, _l, _i, _p],
     "mg_zero_ring": [_p, _i, _i, _l, _i, _i, _i, _p],
+    "mg_cm_workspace_doubles": [],
+    "mg_cm_gs": [_p, _p, _i, _i, _l, _l, _d, _i, _p],
+    "mg_cm_residual": [_p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _d, _p],
+    "mg_cm_diff_sumsq": [_p, _p, _p, _p, _i, _i, _l, _l, _p],
+    "mg_cm_restrict": [_p, _p, _i, _i, _i, _i, _l, _l, _p],
+    "mg_cm_prolong_add": [_p, _p, _i, _i, _i, _i, _l, _l, _p],
     "mg_heat_rhs": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _l, _l, _l, _d, _d, _d, _d, _d, _d, _i, _i, _i, _i, _p],
     "mg_fill_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p],
     "mg_maxerr_sinsin": [_p, _i, _i, _l, _d, _d, _d, _d, _d, _d, _d, _i, _p, _p, _p],
@@ -66,7 +72,7 @@ SIGNATURES = {
 VC_PROLONG, VC_RESTRICT, VC_NORM, VC_LOADER_CPASYNC, VC_NO_STORE, VC_U_ZERO, VC_JACOBI = 1, 2, 4, 16, 32, 64, 128
 _RESTYPE = {"mg_status_string": C.c_char_p, "mg_launch_count": C.c_longlong}
 _NO_STATUS = {"mg_abi_version", "mg_launch_count", "mg_status_string", "mg_device_sm_count", "mg_sumsq_workspace_doubles",
-              "mg_vc_workspace_doubles", "mg_small_cycle_smem_bytes"}
+              "mg_vc_workspace_doubles", "mg_small_cycle_smem_bytes", "mg_cm_workspace_doubles"}
 
 _lib: Optional[C.CDLL] = None
 

@@ -120,6 +120,12 @@ __device__ __forceinline__ double block_reduce(double v, double* red) {
   return x;
 }
 
+// argument check of the C-ABI entry points
+#define MG_REQUIRE(cond)               \
+  do {                                 \
+    if (!(cond)) return MG_ERR_BADARG; \
+  } while (0)
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 int check_launch(const char* what, int launches = 1);  // defined in mg_basic.cu; also counts kernel launches
 int sm_count();

@@ -287,6 +287,7 @@ class DistributedCycleEngine:
                                                  coarse_tolerance, coarse_max_iterations, **ckw)
         self._kw = {"shift": self.shift} if self.shift else {}  # forwarded to every slab pass
         self.exchanges = 0
+        self.phase_events: Optional[List[Any]] = None  # a list while an eager run is being phase-timed (_phase)
 
     # -- buffer roles (for CUDA-graph replay) ---------------------------------------------------------------
     def _all_bufs(self):
@@ -368,6 +369,33 @@ class DistributedCycleEngine:
         return b
 
     # -- communication ------------------------------------------------------------------------------------
+    # -- optional phase timing (eager runs only): CUDA events around the communication steps and the agglomerated tail
+    def _phase(self, name: str):
+        eng = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                self_inner.on = eng.phase_events is not None
+                if self_inner.on:
+                    self_inner.a = torch.cuda.Event(enable_timing=True)
+                    self_inner.a.record()
+
+            def __exit__(self_inner, *exc):
+                if self_inner.on:
+                    b = torch.cuda.Event(enable_timing=True)
+                    b.record()
+                    eng.phase_events.append((name, self_inner.a, b))
+                return False
+        return _Ctx()
+
+    def phase_summary(self) -> Dict[str, float]:
+        """Total milliseconds per phase name of the events recorded since `phase_events` was set to a list."""
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        for name, a, b in self.phase_events or []:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        return out
+
     def exchange(self, t: torch.Tensor, l: int) -> None:
         """Refresh the ghost rows of one level-l local array from the neighbouring slabs."""
         self.exchange_many([(t, l)])
@@ -378,6 +406,10 @@ class DistributedCycleEngine:
             self.valid[t.data_ptr()] = self.part.ghost
         if self.world == 1 or not items:
             return
+        with self._phase("halo_exchange"):
+            self._exchange_now(items)
+
+    def _exchange_now(self, items) -> None:
         if self.transport is not None:
             self.transport.exchange(self.part, items)
             self.exchanges += 1
@@ -425,7 +457,8 @@ class DistributedCycleEngine:
 
     def allreduce_sum(self, x: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
-            dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
+            with self._phase("norm_allreduce"):
+                dist.all_reduce(x, op=dist.ReduceOp.SUM, group=self.group)
         return x
 
     # -- agglomerated levels --------------------------------------------------------------------------------
@@ -441,17 +474,19 @@ class DistributedCycleEngine:
             if self.world == 1:
                 cb.f.copy_(b.f)
             else:
-                # every rank contributes rows [own_lo, own_lo + per]: `per` owned rows plus one more (the boundary
-                # row on the last rank; elsewhere a ghost row that is ignored below)
-                mine = _pitched_rows(b.f, lo, lo + per + 1).contiguous()
-                chunks = [torch.empty_like(mine) for _ in range(self.world)]
-                dist.all_gather(chunks, mine, group=self.group)
-                ny = s.ny
-                for p in range(self.world):
-                    cb.f[p * per:(p + 1) * per].copy_(chunks[p][:per, :ny])
-                cb.f[self.world * per].copy_(chunks[self.world - 1][per, :ny])
-        full_u = self.coarse.cycle(dtype, u_zero)
-        b.u.copy_(full_u[s.row0:s.row0 + s.loc_nx])
+                with self._phase("agglomeration_gather"):
+                    # every rank contributes rows [own_lo, own_lo + per]: `per` owned rows plus one more (the
+                    # boundary row on the last rank; elsewhere a ghost row that is ignored below)
+                    mine = _pitched_rows(b.f, lo, lo + per + 1).contiguous()
+                    chunks = [torch.empty_like(mine) for _ in range(self.world)]
+                    dist.all_gather(chunks, mine, group=self.group)
+                    ny = s.ny
+                    for p in range(self.world):
+                        cb.f[p * per:(p + 1) * per].copy_(chunks[p][:per, :ny])
+                    cb.f[self.world * per].copy_(chunks[self.world - 1][per, :ny])
+        with self._phase("agglomerated_sub_cycle"):
+            full_u = self.coarse.cycle(dtype, u_zero)
+            b.u.copy_(full_u[s.row0:s.row0 + s.loc_nx])
         self.set_valid(b.u, self.part.ghost)  # cut out of the full correction: every ghost row is exact
 
     # -- the recursion ----------------------------------------------------------------------------------------
@@ -971,9 +1006,17 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     ops.TIMER = ops.KernelTimer(min_points=sol.s0.loc_nx * ny // 2) if rank == 0 else None
     launches0 = _lib.call("mg_launch_count")
     ex0 = sol.eng.exchanges
+    sol.eng.phase_events = []
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_eager = time.perf_counter()
     for _ in range(a.steps):
         step()
     torch.cuda.synchronize()
+    t_eager = (time.perf_counter() - t_eager) * 1e3 / max(1, a.steps)
+    phases = {k: round(v / max(1, a.steps), 4) for k, v in sol.eng.phase_summary().items()}
+    phases["eager_step_wall"] = round(t_eager, 4)
+    sol.eng.phase_events = None
     dist.barrier()
     launches = _lib.call("mg_launch_count") - launches0
     ex_per_step = (sol.eng.exchanges - ex0) / max(1, a.steps)
@@ -1040,6 +1083,9 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                    "levels": sol.eng.num_levels, "distributed_levels": sol.eng.D, "ghost_rows": sol.eng.part.ghost,
                    "agglomerated_grid": list(sol.eng.part.agg_shape), "tolerance": tol,
                    "halo_exchanges_per_step": ex_per_step, "halo": getattr(a, "halo", "nccl"),
+                   # rank 0, eager replay of the timed steps with CUDA events around the communication steps and the
+                   # agglomerated tail (ms per step; the level passes are in `kernels`)
+                   "phases_ms_per_step_eager": phases,
                    "cuda_graphs": (not a.no_graphs),
                    "graphs_captured": sol.graphs.captured, "priming_solves": primed,
                    "l2": "slab arrays (>= 1 GB) exceed the 126 MB L2; no flush needed",
