@@ -169,6 +169,10 @@ class DeviceBackend:
             k["workspace"] = self._workspace(f)
         return self.ops.vc_defect_pass(u_in, u_out, f, *a, loader=self.loader, **k)
 
+    def vc_defect_down_pass(self, u_in, u_out, f, *a, **k):
+        k["workspace"] = self._workspace(f)
+        return self.ops.vc_defect_down_pass(u_in, u_out, f, *a, **k)
+
     def zero_ring(self, t, first_row: bool, last_row: bool):
         self.ops.zero_ring_(t, first_row, last_row)
 
@@ -499,8 +503,11 @@ class DistributedCycleEngine:
             return max(1, 2 ** (self.num_levels - l - 2))
         return 0
 
-    def cycle(self, dtype, l: int = 0, u_zero: bool = False, sumsq_out: Optional[torch.Tensor] = None) -> None:
-        """One cycle on distributed level l (all distributed levels in `dtype`)."""
+    def cycle(self, dtype, l: int = 0, u_zero: bool = False, sumsq_out: Optional[torch.Tensor] = None,
+              skip_down: bool = False) -> None:
+        """One cycle on distributed level l (all distributed levels in `dtype`).  ``skip_down`` (level 0 only): the
+        caller's fused defect + down pass has already left the pre-smoothed iterate in b.u and the restricted
+        residual in the next level's f (with their ghost validity recorded)."""
         if l == self.D:
             self._agglomerated_cycle(dtype, u_zero)
             return
@@ -513,7 +520,7 @@ class DistributedCycleEngine:
         ms = 1 if (self.coefficient is not None and dtype == torch.float64) else 2
         # down: `pre` sweeps, the last pass with residual + restriction; dependency cone of a pass = 2 rows per sweep
         # (+2 for the owned coarse rows of the restriction)
-        n, uz = self.pre, u_zero
+        n, uz = (0 if skip_down else self.pre), u_zero
         while n > 0:
             k = min(n, ms)
             last = n - k == 0
@@ -597,7 +604,7 @@ class DistributedMixedPrecisionSolver:
     def __init__(self, nx: int, ny: int, *, domain=(0.0, 1.0, 0.0, 1.0), precision_strategy: str = "adaptive",
                  switch_threshold: float = 1e-6, tolerance: float = 1e-8, max_iterations: int = 50, backend=None,
                  device=None, use_cuda_graphs: bool = False, stagnation_ratio: float = 0.95,
-                 stop_on_rounding_floor: bool = True, **engine_kw):
+                 stop_on_rounding_floor: bool = True, use_fused_defect_down: bool = True, **engine_kw):
         self.eng = DistributedCycleEngine(nx, ny, domain=domain, backend=backend, device=device, **engine_kw)
         self.mode = {"double": "fp64", "fp64": "fp64", "single": "fp32", "fp32": "fp32", "refinement": "refine"}.get(
             precision_strategy, "switch")
@@ -608,6 +615,7 @@ class DistributedMixedPrecisionSolver:
         self.hxhy = s0.hx * s0.hy
         self.ss = self.eng.be.scalar(2)
         self.phase = None
+        self.fused_defect_down = bool(use_fused_defect_down) and self._dd_ok()
         self.precision_switches: List[Dict[str, Any]] = []
         for l in range(self.eng.D + 1):  # final shape of the buffer-role state before the first step
             for dt in ((torch.float64, torch.float32) if self.mode in ("switch", "refine") else
@@ -694,6 +702,9 @@ class DistributedMixedPrecisionSolver:
         return self._norm(1)
 
     def _launch_defect(self, with_update: bool, u_zero: bool = False) -> None:
+        if self.fused_defect_down:
+            self._launch_defect_down(with_update, u_zero)
+            return
         eng, s = self.eng, self.s0
         b64, b32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32)
         kw = eng._var_kw(0, torch.float64)
@@ -717,8 +728,43 @@ class DistributedMixedPrecisionSolver:
         eng.allreduce_sum(self.ss)
 
     def _launch_refine(self, u_zero: bool = False) -> None:
-        self.eng.cycle(torch.float32, 0, u_zero=True)
+        if self.fused_defect_down:  # the down pass of this cycle ran inside the previous defect pass
+            self.eng.cycle(torch.float32, 0, u_zero=True, skip_down=True)
+        else:
+            self.eng.cycle(torch.float32, 0, u_zero=True)
         self._launch_defect(True, u_zero)
+
+    def _dd_ok(self) -> bool:
+        """The refinement cycle can use the fused defect + down pass (ops.vc_defect_down_pass) on the slabs: constant
+        coefficients, two pre-smoothing sweeps, at least one distributed level below level 0, a back end that has it."""
+        eng = self.eng
+        return (self.mode in ("switch", "refine") and eng.coefficient is None and eng.pre == 2 and eng.D >= 1
+                and hasattr(eng.be, "vc_defect_down_pass") and getattr(eng.be, "loader", "tma") == "tma")
+
+    def _launch_defect_down(self, with_update: bool, u_zero: bool) -> None:
+        """u64 += e32 ; r32 ; ||r|| over the owned rows ; e' = 2 sweeps from zero on A e = r32 ; f_c = R(r32 - A e')
+        in ONE pass over the slab.  Ghost validity: the update is pointwise, the residual reaches one row, two
+        sweeps four more, the restriction two more (and halves)."""
+        eng, s = self.eng, self.s0
+        b64, b32, c32 = eng.bufs(0, torch.float64), eng.bufs(0, torch.float32), eng.bufs(1, torch.float32)
+        off, rows = eng.part.coarse_view(0)
+        G = eng.part.ghost
+        self.ss.zero_()
+        ins = [(b64.f, 0)] + ([] if u_zero else [(b64.u, 0)]) + ([(b32.u, 0)] if with_update else [])
+        eng.ensure(7, ins)
+        v = min(eng.vdepth(t) for t, _ in ins)
+        eng.be.vc_defect_down_pass(b64.u, b64.tmp if with_update else None, b64.f, s.hx, s.hy,
+                                   e_in=b32.u if with_update else None, r_out=b32.f, e_out=b32.tmp,
+                                   coarse_out=c32.f[off:off + rows], sumsq_out=self.ss[1:2], u_zero=u_zero,
+                                   norm_rows=s.own_local, shift=eng.shift)
+        if with_update:
+            b64.u, b64.tmp = b64.tmp, b64.u
+            eng.set_valid(b64.u, min(G if u_zero else eng.vdepth(b64.tmp), eng.vdepth(b32.u)))
+        b32.u, b32.tmp = b32.tmp, b32.u
+        eng.set_valid(b32.f, v - 1)
+        eng.set_valid(b32.u, v - 1 - 4)
+        eng.set_valid(c32.f, (v - 1 - 6) // 2)
+        eng.allreduce_sum(self.ss)
 
     def _launch_uniform(self, dt, u_zero: bool = False) -> None:
         self.ss.zero_()
@@ -958,6 +1004,7 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
                                           tolerance=tol, cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader),
                                           device=dev, use_cuda_graphs=not a.no_graphs,
                                           agglomerate_below=_bench_agg(a),
+                                          use_fused_defect_down=not getattr(a, "no_dd", False),
                                           ghost=getattr(a, "ghost", None) or BENCH_GHOST, **_halo_kw(a, dev))
     sol.set_rhs_sinsin_device()
     sol.zero_boundary_ring_of_rhs()
@@ -1031,8 +1078,12 @@ def run_distributed_bench(a, world: int, rank: int, dev, peak: float, peak_src: 
     for tag, d in sorted(kern.items(), key=lambda kv: -kv[1]["total_ms"]):
         name, dtn, _ = tag.split("/")
         w = 8 if dtn == "f64" else 4
+        fused = name.startswith("dd:")  # fused defect + down pass: the defect pass's traffic + e' and f_c written
+        if fused:
+            name = name[3:]
         if "resid32" in name or "update" in name:  # defect pass: read u64, f64, write r32 (+ read e32, write u64)
             b = (20 if "resid32" in name else 0) + (12 if "update" in name else 0) - (8 if name.startswith("Z+") else 0)
+            b += 5 if fused else 0
         else:
             b = 3.0 * w - (w if name.startswith("Z+") else 0) + (0.25 * w if "P+" in name else 0) + (0.25 * w if "+R" in name else 0)
         ach = b * pts / (d["mean_ms"] * 1e-3) / 1e9

@@ -151,3 +151,13 @@ class OracleBackend:
             r_out.copy_(torch.from_numpy(R.astype(np.float32)))
             lo, hi = norm_rows if norm_rows is not None else (0, U.shape[0])
             sumsq_out[0] = float(np.sum(R[lo:hi] ** 2))
+
+    def vc_defect_down_pass(self, u_in, u_out, f, hx, hy, *, e_in=None, r_out=None, e_out=None, coarse_out=None,
+                            sumsq_out=None, omega=1.0, coefficient=-1.0, shift=0.0, u_zero=False, norm_rows=None, rows=0,
+                            workspace=None):
+        """The fused defect + down pass is, by construction, the defect pass followed by the first pass of the fp32
+        error cycle (two sweeps from zero, residual, restriction)."""
+        self.vc_defect_pass(u_in, u_out, f, hx, hy, e_in=e_in, r_out=r_out, sumsq_out=sumsq_out, coefficient=coefficient,
+                            norm_rows=norm_rows, shift=shift, u_zero=u_zero)
+        self.vc_pass(None, e_out, r_out, hx, hy, sweeps=2, omega=omega, coefficient=coefficient, coarse_out=coarse_out,
+                     u_zero=True, shift=shift)
