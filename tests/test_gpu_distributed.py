@@ -119,3 +119,26 @@ def test_world1_distributed_variable_coefficients_match_the_single_gpu_facade():
         assert info["converged"] and info["iterations"] == si["iterations"], (info["iterations"], si["iterations"])
         np.testing.assert_allclose(info["residual_history"], si["residual_history"], rtol=1e-6)
         assert np.max(np.abs(u.cpu().numpy() - us)) <= 1e-11 * np.max(np.abs(us))
+
+
+def test_world1_solve_many_on_slabs_is_solve_per_right_hand_side():
+    """The pipelined batch API of the slab solver (pinned host slabs in, pinned host slabs out, transfers overlapping the
+    cycles): every solution equals the one `solve()` returns for that right-hand side, bit for bit."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedMixedPrecisionSolver
+    n = 513
+    sol = DistributedMixedPrecisionSolver(n, n, precision_strategy="adaptive", tolerance=1e-8, agglomerate_below=65,
+                                          device=torch.device("cuda", 0), use_cuda_graphs=True)
+    base = torch.from_numpy(O.mms_rhs(n))
+    fs = [(base * s).pin_memory() for s in (1.0, -2.5, 0.5, 3.0)]
+    us = [torch.empty((n, n), dtype=torch.float64).pin_memory() for _ in fs]
+    infos = sol.solve_many(fs, us)
+    torch.cuda.synchronize()
+    assert len(infos) == 4 and all(i["converged"] for i in infos)
+    for f, u in zip(fs, us):
+        sol.set_rhs_from_global(f.cuda())
+        ref, info = sol.solve()
+        assert torch.equal(ref.cpu(), u)
+    err = np.max(np.abs(us[0].numpy() - O.mms_exact(n)))
+    assert abs(err - O.mms_discretisation_error(n)) <= 0.01 * O.mms_discretisation_error(n)
+    with pytest.raises(ValueError):
+        sol.solve_many(fs, us[:2])
