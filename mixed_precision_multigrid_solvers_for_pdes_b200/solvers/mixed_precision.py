@@ -512,13 +512,27 @@ class MixedPrecisionMultigrid:
         if was_np:
             if self._pinned_out is None or tuple(self._pinned_out.shape) != (nx, ny):
                 self._pinned_out = torch.empty((nx, ny), dtype=torch.float64, pin_memory=True)
-            self._pinned_out.copy_(u_dev, non_blocking=True)
-            torch.cuda.current_stream(eng.dev).synchronize()
             if reuse_output:
+                self._pinned_out.copy_(u_dev, non_blocking=True)
+                torch.cuda.current_stream(eng.dev).synchronize()
                 solution = self._pinned_out.numpy()
-            else:  # owned result: torch's multi-threaded host copy (a NumPy .copy() of 2 GB takes 0.4 s on one core)
+            else:
+                # owned result: the download goes out in row chunks of ~128 MB, and each chunk is copied from the
+                # pinned staging buffer into the caller's array (torch's multi-threaded host copy; a NumPy .copy() of
+                # 2 GB takes 0.4 s on one core) while the next chunks are still crossing PCIe
                 owned = torch.empty((nx, ny), dtype=torch.float64)
-                owned.copy_(self._pinned_out)
+                rows = max(1, min(nx, (128 << 20) // (8 * ny)))
+                cur = torch.cuda.current_stream(eng.dev)
+                marks = []
+                for r0 in range(0, nx, rows):
+                    r1 = min(nx, r0 + rows)
+                    self._pinned_out[r0:r1].copy_(u_dev[r0:r1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    marks.append((r0, r1, ev))
+                for r0, r1, ev in marks:
+                    ev.synchronize()
+                    owned[r0:r1].copy_(self._pinned_out[r0:r1])
                 solution = owned.numpy()
         else:
             solution = u_dev.clone()
