@@ -373,7 +373,7 @@ def gpu_arm(a):
         ph, first = pol.phase, state["first"]
         state["first"] = False
         if ph == "refine":
-            norm = solver._cycle_refinement(u_zero=first)
+            norm = solver._cycle_refinement(u_zero=first, last_hint=pol.likely_last())
         elif ph == "fp64":
             norm = solver._cycle_fp64(u_zero=first)
         else:

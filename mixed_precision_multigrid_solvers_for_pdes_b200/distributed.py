@@ -629,6 +629,7 @@ class DistributedMixedPrecisionSolver:
         self.ss = self.eng.be.scalar(2)
         self.phase = None
         self.fused_defect_down = bool(use_fused_defect_down) and self._dd_ok()
+        self._pre_smoothed = False
         self.precision_switches: List[Dict[str, Any]] = []
         for l in range(self.eng.D + 1):  # final shape of the buffer-role state before the first step
             for dt in ((torch.float64, torch.float32) if self.mode in ("switch", "refine") else
@@ -712,10 +713,11 @@ class DistributedMixedPrecisionSolver:
     def _defect(self, with_update: bool, u_zero: bool = False) -> float:
         self.graphs.run(("defect_u" if with_update else "defect") + ("0" if u_zero else ""),
                         lambda: self._launch_defect(with_update, u_zero))
+        self._pre_smoothed = self.fused_defect_down
         return self._norm(1)
 
-    def _launch_defect(self, with_update: bool, u_zero: bool = False) -> None:
-        if self.fused_defect_down:
+    def _launch_defect(self, with_update: bool, u_zero: bool = False, fuse_next: bool = True) -> None:
+        if self.fused_defect_down and fuse_next:
             self._launch_defect_down(with_update, u_zero)
             return
         eng, s = self.eng, self.s0
@@ -740,12 +742,14 @@ class DistributedMixedPrecisionSolver:
         eng.set_valid(b32.f, min(v, eng.vdepth(b64.f)) - 1)
         eng.allreduce_sum(self.ss)
 
-    def _launch_refine(self, u_zero: bool = False) -> None:
-        if self.fused_defect_down:  # the down pass of this cycle ran inside the previous defect pass
+    def _launch_refine(self, u_zero: bool = False, pre_smoothed: bool = True, fuse_next: bool = True) -> None:
+        """pre_smoothed: the down pass of this cycle ran inside the previous defect pass; fuse_next: this cycle's defect
+        pass also runs the down pass of the next cycle (skipped when the policy expects this cycle to be the last)."""
+        if self.fused_defect_down and pre_smoothed:
             self.eng.cycle(torch.float32, 0, u_zero=True, skip_down=True)
         else:
             self.eng.cycle(torch.float32, 0, u_zero=True)
-        self._launch_defect(True, u_zero)
+        self._launch_defect(True, u_zero, fuse_next)
 
     def _dd_ok(self) -> bool:
         """The refinement cycle can use the fused defect + down pass (ops.vc_defect_down_pass) on the slabs: constant
@@ -789,7 +793,14 @@ class DistributedMixedPrecisionSolver:
         the policy (solvers/policy.py) made of it: 'continue', 'converged' or 'rounding_floor'."""
         first = self._fresh and not self.history
         if self.phase == "refine":
-            self.graphs.run("refine0" if first else "refine", lambda: self._launch_refine(first))
+            if self.fused_defect_down:
+                # every rank sees the same all-reduced norms, so every rank takes the same variant
+                pre, fuse = self._pre_smoothed, not self.policy.likely_last()
+                key = "refine" + ("_dd" if pre else "_full") + ("" if fuse else "_last") + ("0" if first else "")
+                self.graphs.run(key, lambda: self._launch_refine(first, pre, fuse))
+                self._pre_smoothed = fuse
+            else:
+                self.graphs.run("refine0" if first else "refine", lambda: self._launch_refine(first))
             norm = self._norm(1)
         else:
             dt = torch.float64 if self.phase == "fp64" else torch.float32

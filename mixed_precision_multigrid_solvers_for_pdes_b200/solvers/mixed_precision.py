@@ -170,6 +170,7 @@ class MixedPrecisionMultigrid:
             post=self.post, kernels=self.kernels, loader=self.loader, device=dev)
         self._shape, self._domain, self._grid = (nx, ny), tuple(domain), g
         self._dd_cache = None
+        self._pre_smoothed = False
         self._sumsq = torch.zeros(2, dtype=torch.float64, device=dev)
         self._pinned_out = None
         eng = self._engine
@@ -224,6 +225,7 @@ class MixedPrecisionMultigrid:
         With the fused defect + down pass (see `_dd_ok`) the same launch also pre-smooths the next error equation."""
         if self._dd_ok():
             self._graphed("dd0_0" if u_zero else "dd0", lambda: self._launch_defect_down(with_update, u_zero))
+            self._pre_smoothed = True
         else:
             self._launch_refinement_residual(with_update, u_zero)
         return self._norm_from(self._sumsq[1:2])
@@ -263,10 +265,17 @@ class MixedPrecisionMultigrid:
             b64.u, b64.tmp = b64.tmp, b64.u
         b32.u, b32.tmp = b32.tmp, b32.u  # b32.u = the pre-smoothed error iterate, as after the down pass
 
-    def _launch_refinement_cycle_dd(self, u_zero: bool = False) -> None:
-        # the down pass of this cycle ran inside the previous defect pass: coarse levels + up pass, then the next one
-        self._engine.cycle(self._inner_dtypes(), 0, None, skip_down=True)
-        self._launch_defect_down(True, u_zero)
+    def _launch_refinement_cycle_dd(self, u_zero: bool = False, pre_smoothed: bool = True, fuse_next: bool = True) -> None:
+        # pre_smoothed: the down pass of this cycle ran inside the previous defect pass -> coarse levels + up pass only;
+        # fuse_next: the defect pass of this cycle also runs the down pass of the next one
+        if pre_smoothed:
+            self._engine.cycle(self._inner_dtypes(), 0, None, skip_down=True)
+        else:
+            self._engine.cycle(self._inner_dtypes(), 0, None, u_zero=True)
+        if fuse_next:
+            self._launch_defect_down(True, u_zero)
+        else:
+            self._launch_refinement_residual(True, u_zero)
 
     def _launch_refinement_residual(self, with_update: bool, u_zero: bool = False) -> None:
         eng, g = self._engine, self._grid
@@ -298,11 +307,19 @@ class MixedPrecisionMultigrid:
         self._engine.cycle(self._inner_dtypes(), 0, None, u_zero=True)
         self._launch_refinement_residual(True, u_zero)
 
-    def _cycle_refinement(self, u_zero: bool = False) -> float:
+    def _cycle_refinement(self, u_zero: bool = False, last_hint: bool = False) -> float:
         """One fp32 cycle on A e = r32 (e0 = 0, never read), then u64 += e32 fused with the next residual.
-        ``u_zero``: first cycle of a solve from the zero initial guess (u64 = e32, the iterate is not read)."""
+        ``u_zero``: first cycle of a solve from the zero initial guess (u64 = e32, the iterate is not read).
+        ``last_hint`` (CyclePolicy.likely_last): this cycle probably ends the solve, so its defect pass does not
+        pre-smooth the next error equation; if the solve goes on after all, the next cycle starts with its own down
+        pass (`_pre_smoothed` keeps track).  Results do not depend on the hint: the fused pass and the two launches
+        are bit-identical."""
         if self._dd_ok():
-            self._graphed("refine_dd_0" if u_zero else "refine_dd", lambda: self._launch_refinement_cycle_dd(u_zero))
+            pre = self._pre_smoothed
+            fuse_next = not last_hint
+            key = "refine" + ("_dd" if pre else "_full") + ("" if fuse_next else "_last") + ("_0" if u_zero else "")
+            self._graphed(key, lambda: self._launch_refinement_cycle_dd(u_zero, pre, fuse_next))
+            self._pre_smoothed = fuse_next
         else:
             self._graphed("refine_0" if u_zero else "refine", lambda: self._launch_refinement_cycle(u_zero))
         return self._norm_from(self._sumsq[1:2])
@@ -409,7 +426,8 @@ class MixedPrecisionMultigrid:
             phase = pol.phase
             first = fresh and iteration == 1
             if phase == "refine":
-                norm = self._cycle_refinement(u_zero=first)  # residual of the new iterate (also next cycle's rhs)
+                # residual of the new iterate (also next cycle's right-hand side)
+                norm = self._cycle_refinement(u_zero=first, last_hint=pol.likely_last())
             elif phase == "fp64":
                 norm = self._cycle_fp64(u_zero=first)
             else:

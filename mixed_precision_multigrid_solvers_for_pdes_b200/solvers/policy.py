@@ -97,6 +97,20 @@ class CyclePolicy:
         self._floor_hits += 1
         return self._floor_hits >= self.floor_confirmations
 
+    def likely_last(self) -> bool:
+        """A HINT for the driver of the fused defect + down pass: the cycle about to run will probably end the solve
+        (its norm meets the tolerance if it contracts like the last one did, or it is the confirming cycle on the
+        rounding floor), so pre-smoothing the NEXT error equation inside its defect pass would be wasted work.
+        Wrong guesses cost nothing but that one saving: the driver then runs the pre-smoothing as its own pass."""
+        h = self.history
+        if self.phase != "refine" or not h:
+            return False
+        if self._floor_hits > 0 and self._floor_hits >= self.floor_confirmations - 1:
+            return True
+        if self.stop_on_floor and self.floor_bound is not None and self.tolerance < self.floor_bound:
+            return False  # this solve ends on the rounding floor, not on the tolerance: wait for the floor hits
+        return len(h) >= 2 and h[-2] > 0 and h[-1] * min(1.0, h[-1] / h[-2]) < self.tolerance
+
     def _bound(self) -> float:
         if self.floor_bound is None:
             self.floor_bound = residual_floor_bound(self.hx, self.hy, self.shift, self.u_norm(self.phase), "fp64")

@@ -379,3 +379,25 @@ def test_defect_down_refinement_matches_two_pass_refinement():
     assert len(hist[0][0]) >= 8 and len(hist[0][0]) == len(hist[1][0])
     np.testing.assert_allclose(hist[0][0], hist[1][0], rtol=1e-12)
     assert np.array_equal(hist[0][1], hist[1][1])
+
+
+def test_last_cycle_hint_never_changes_results():
+    """`last_hint` only chooses between the fused pass and its two launches (bit-identical): any sequence of hints,
+    right or wrong, walks through the same iterates as the two-launch cycle."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200 import MixedPrecisionMultigrid
+    n = 1025
+    out = []
+    for dd, hints in ((False, [False] * 6), (True, [False, True, True, False, True, False]), (True, [True] * 6)):
+        s = MixedPrecisionMultigrid(precision_strategy="refinement", tolerance=1e-30, use_fused_defect_down=dd,
+                                    use_cuda_graphs=True)
+        s.setup(n, n)
+        b64 = s._engine.levels[0].bufs(torch.float64)
+        ops.fill_sinsin_(b64.f, (0.0, 1.0, 0.0, 1.0), 2 * np.pi ** 2, 1.0, 1.0)
+        ops.zero_ring_(b64.f)
+        norms = [s._refinement_residual(u_zero=True)]
+        for k, h in enumerate(hints):
+            norms.append(s._cycle_refinement(u_zero=(k == 0), last_hint=h))
+        out.append((norms, s._engine.levels[0].bufs(torch.float64).u.clone()))
+    for norms, u in out[1:]:
+        np.testing.assert_allclose(norms, out[0][0], rtol=1e-12)
+        assert torch.equal(u, out[0][1])

@@ -145,3 +145,25 @@ def test_policy_stagnating_refinement_is_promoted_then_ends_on_the_floor():
     assert acts[-1] == mod.FLOOR and q.phase == "refine"
     with __import__("pytest").raises(ValueError):
         _policy("half")
+
+
+def test_policy_last_cycle_hint():
+    """CyclePolicy.likely_last: true before a cycle that should meet the tolerance at the last contraction rate, and
+    before the confirming cycle on the rounding floor; never in the fp64 phase."""
+    from mixed_precision_multigrid_solvers_for_pdes_b200.solvers.policy import CONTINUE, CyclePolicy
+    p = CyclePolicy("refine", 1e-8, 1e-6, 1 / 1024, 1 / 1024, u_norm=lambda phase: 0.5)
+    assert not p.likely_last()
+    for norm, expect in ((1e-1, False), (1e-2, False), (1e-3, False), (1e-4, False), (1e-5, False), (1e-6, False),
+                         (5e-8, True)):
+        assert p.observe(norm) == CONTINUE
+        assert p.likely_last() == expect, norm
+    # rounding floor: h = 1/16384 -> bound 1.2e-7 * ||u||; the first stagnating cycle arms the hint
+    q = CyclePolicy("refine", 1e-8, 1e-6, 1 / 16384, 1 / 16384, u_norm=lambda phase: 0.5)
+    for norm in (1e-2, 1e-3, 1e-4, 1e-5, 1e-6, 1.2e-7):
+        assert q.observe(norm) == CONTINUE
+    assert not q.likely_last()
+    assert q.observe(6.5e-8) == CONTINUE and q._floor_hits == 1 and q.likely_last()
+    assert q.observe(5.9e-8) == "rounding_floor"
+    r = CyclePolicy("fp64", 1e-8, 1e-6, 1 / 1024, 1 / 1024)
+    r.observe(1e-3), r.observe(5e-8)
+    assert not r.likely_last()

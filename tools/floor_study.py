@@ -38,7 +38,7 @@ def main():
             s._refinement_residual(u_zero=True)
         for k in range(1, cycles + 1):
             ph = pol.phase
-            norm = s._cycle_refinement(u_zero=first) if ph == "refine" else s._cycle_fp64(u_zero=first)
+            norm = s._cycle_refinement(u_zero=first, last_hint=pol.likely_last()) if ph == "refine" else s._cycle_fp64(u_zero=first)
             first = False
             pol.observe(norm)
             err = ops.maxerr_sinsin(s._engine.levels[0].bufs(torch.float64).u)
