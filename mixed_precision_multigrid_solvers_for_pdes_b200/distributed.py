@@ -711,9 +711,12 @@ class DistributedMixedPrecisionSolver:
         return float(np.sqrt(self.hxhy * self.ss[slot].item()))
 
     def _defect(self, with_update: bool, u_zero: bool = False) -> float:
+        # from the zero iterate the residual is f itself: two launches beat the fused pass there (see
+        # MixedPrecisionMultigrid._refinement_residual)
+        fuse = self.fused_defect_down and not (u_zero and not with_update)
         self.graphs.run(("defect_u" if with_update else "defect") + ("0" if u_zero else ""),
-                        lambda: self._launch_defect(with_update, u_zero))
-        self._pre_smoothed = self.fused_defect_down
+                        lambda: self._launch_defect(with_update, u_zero, fuse))
+        self._pre_smoothed = fuse
         return self._norm(1)
 
     def _launch_defect(self, with_update: bool, u_zero: bool = False, fuse_next: bool = True) -> None:
