@@ -16,14 +16,17 @@ template <> struct Stages<double> { static constexpr int N = 2; };
 // Rows per tile.  A warp streams R + lead + tail rows sequentially, so a launch lasts about
 // waves * (R + overlap) row-steps, with waves = warps needed / warps resident.  Large grids want tall tiles
 // (overlap amortised), small grids want short ones (short critical path, all SMs busy) -- but never taller than
-// 128 rows: measured on 16385^2 (tools/bench_dd.py, profiles/r02_dd_tile_sweep.log) every pass slows down beyond
-// that (256 rows: +3..12 %, 512 rows: +7..33 %; tiles that fill whole waves exactly, e.g. 514 rows, too), because
-// short tiles keep the rows that are streamed concurrently close together in memory and the halo rows in L2.
+// 64 rows.  Measured (tools/bench_dd.py; profiles/r02_dd_tile_sweep.log, r02_rows_sweep_all_passes.log,
+// r02_rows_sweep_coarse_levels.log): on 16385^2 every pass is flat between 48 and 96 rows, 1-2 % slower at 128, +3..12 %
+// at 256 and +7..33 % at 512 rows (tiles that fill whole waves exactly, e.g. 514 rows, too); on 8193^2 (level 1 of
+// the benchmarked cycle, level 0 of the heat runs) 128 rows cost 4-13 % against 48-64; on 4097^2 32-64 rows are
+// best.  Short tiles keep the rows that are streamed concurrently close together (column halos hit L2) and leave
+// a short tail when the last wave of CTAs is only partly filled.
 static inline int pick_rows(int nx, int nstrips, int overlap) {
   const int64_t capacity = (int64_t)sm_count() * 12;  // resident warps (3 blocks of 4 warps per SM)
-  int best = 128;
+  int best = 64;
   int64_t best_cost = INT64_MAX;
-  for (int r = 128; r >= 8; r >>= 1) {
+  for (int r = 64; r >= 8; r >>= 1) {
     const int64_t warps = (int64_t)nstrips * ((nx + r - 1) / r);
     const int64_t waves = (warps + capacity - 1) / capacity;
     const int64_t cost = waves * (r + overlap);

@@ -53,7 +53,7 @@ for rows in ROWS:
         ops.vc_pass(tmp, eo, r, h, h, sweeps=2, coarse_out=co, u_zero=True, rows=rows)
 
     def up():
-        ops.vc_pass(eo, tmp, r, h, h, sweeps=2, coarse_in=co)
+        ops.vc_pass(eo, tmp, r, h, h, sweeps=2, coarse_in=co, rows=rows)
 
     out = {"n": n, "rows": rows, "variant": os.environ.get("MG_DD_VARIANT", "0"), "fused_ms": timed(fused)}
     if os.environ.get("MG_DD_VARIANT", "0") == "0":
