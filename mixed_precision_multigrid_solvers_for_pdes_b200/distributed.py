@@ -628,6 +628,8 @@ class DistributedMixedPrecisionSolver:
         self.hxhy = s0.hx * s0.hy
         self.ss = self.eng.be.scalar(2)
         self.phase = None
+        # the fused pass pays off on large slabs only (see MixedPrecisionMultigrid._dd_ok); "always" forces it (tests)
+        self.fused_defect_down_min_points = 0 if use_fused_defect_down == "always" else 6000 * 6000
         self.fused_defect_down = bool(use_fused_defect_down) and self._dd_ok()
         self._pre_smoothed = False
         self.precision_switches: List[Dict[str, Any]] = []
@@ -759,7 +761,8 @@ class DistributedMixedPrecisionSolver:
         coefficients, two pre-smoothing sweeps, at least one distributed level below level 0, a back end that has it."""
         eng = self.eng
         return (self.mode in ("switch", "refine") and eng.coefficient is None and eng.pre == 2 and eng.D >= 1
-                and hasattr(eng.be, "vc_defect_down_pass") and getattr(eng.be, "loader", "tma") == "tma")
+                and hasattr(eng.be, "vc_defect_down_pass") and getattr(eng.be, "loader", "tma") == "tma"
+                and self.s0.loc_nx * self.s0.ny >= self.fused_defect_down_min_points)
 
     def _launch_defect_down(self, with_update: bool, u_zero: bool) -> None:
         """u64 += e32 ; r32 ; ||r|| over the owned rows ; e' = 2 sweeps from zero on A e = r32 ; f_c = R(r32 - A e')
@@ -1313,12 +1316,14 @@ def _bench_parity_check(a, world: int, rank: int, dev, n: int = 4097) -> Dict[st
     dsol = DistributedMixedPrecisionSolver(n, n, precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
                                            cycle_type=a.cycle, backend=DeviceBackend(dev, a.loader), device=dev,
                                            use_cuda_graphs=False, agglomerate_below=_bench_agg(a),
+                                           # the fused defect + down pass of the timed run, forced on this smaller grid
+                                           use_fused_defect_down=False if getattr(a, "no_dd", False) else "always",
                                            ghost=getattr(a, "ghost", None) or BENCH_GHOST, **_halo_kw(a, dev))
     dsol.set_rhs_from_global(f)
     u, info = dsol.solve()
     full = dsol.eng.gather_solution(u)
     out: Dict[str, Any] = {"grid": [n, n], "cycles_distributed": info["iterations"], "dist_levels": dsol.eng.D,
-                           "ghost_rows": dsol.eng.part.ghost}
+                           "ghost_rows": dsol.eng.part.ghost, "fused_defect_down": bool(dsol.fused_defect_down)}
     if rank == 0:
         single = MixedPrecisionMultigrid(precision_strategy=a.strategy, switch_threshold=1e-6, tolerance=1e-8,
                                          cycle_type=a.cycle, loader=a.loader, device=dev, strict_reference_norm=True)

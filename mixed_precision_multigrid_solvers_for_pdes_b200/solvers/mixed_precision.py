@@ -234,6 +234,8 @@ class MixedPrecisionMultigrid:
         return self._norm_from(self._sumsq[1:2])
 
     # -- fused defect + down pass (mg_stream_dd.cuh): 37 instead of 41 bytes per point and cycle, one launch less ------
+    FUSED_DEFECT_DOWN_MIN_POINTS = 6000 * 6000
+
     def _dd_ok(self) -> bool:
         """The refinement cycle can use ops.vc_defect_down_pass: constant coefficients, red-black GS with two
         pre-smoothing sweeps, TMA loader, level 0 handled by the streaming kernel (not by the small-cycle kernel)."""
@@ -242,7 +244,12 @@ class MixedPrecisionMultigrid:
             eng = self._engine
             dts = self._inner_dtypes()
             hit = False
-            if (self.use_fused_defect_down and self.coefficient is None and eng.kernels != "basic" and eng.loader == "tma"
+            nx0, ny0 = self._shape
+            # measured A/B (bench.py --n N [--no-dd]): 8193^2 -0.7 %, 16385^2 -2.5 % per cycle with the fused pass, but
+            # +4-5 % at 1025^2 ... 4097^2, where a cycle is launch- and latency-bound and the longer dependent chain per
+            # row of the fused kernel costs more than the saved launch
+            big = nx0 * ny0 >= self.FUSED_DEFECT_DOWN_MIN_POINTS or self.use_fused_defect_down == "always"
+            if (self.use_fused_defect_down and big and self.coefficient is None and eng.kernels != "basic" and eng.loader == "tma"
                     and getattr(eng.smoother, "kind", None) == "rbgs" and self.pre == 2 and eng.num_levels >= 3
                     and dts[0] == dts[1] == torch.float32 and not eng._small_ok(0, dts)):
                 b64, b32 = eng.levels[0].bufs(torch.float64), eng.levels[0].bufs(torch.float32)

@@ -32,6 +32,7 @@ def main():
             from mixed_precision_multigrid_solvers_for_pdes_b200.halo import SymmMemTransport
             kw["transport"] = SymmMemTransport(dev, GHOST)
         sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=strategy.split("_")[0],
+                                              use_fused_defect_down="always",
                                               tolerance=1e-8, agglomerate_below=129, device=dev,
                                               use_cuda_graphs=strategy.endswith("graphs"), **kw)
         sol.set_rhs_from_global(torch.from_numpy(f).to(dev))
@@ -67,7 +68,8 @@ def main():
     kx, ky = np.pi / 2.0, np.pi
     mode = lambda X, Y: np.sin(kx * X) * np.sin(ky * Y)  # noqa: E731
     prob = HeatProblem("decay", mode, None, lambda X, Y, t: mode(X, Y) * np.exp(-(kx ** 2 + ky ** 2) * t), domain=dom)
-    hs = DistributedHeatSolver(tolerance=1e-9, agglomerate_below=129, device=dev, use_cuda_graphs=True)
+    hs = DistributedHeatSolver(tolerance=1e-9, agglomerate_below=129, device=dev, use_cuda_graphs=True,
+                               use_fused_defect_down="always")
     r = hs.solve_heat_problem(prob, nx, ny, TimeSteppingConfig(TimeSteppingMethod.BACKWARD_EULER, dt=0.002, t_final=0.007))
     res["heat"] = {"u": r["final_solution"], "iters": r["total_mg_iterations"], "steps": r["total_steps"],
                    "errors": r["errors"], "exchanges": r["halo_exchanges"]}

@@ -89,6 +89,7 @@ def _worker(rank, world, port, case, out):
         elif case["kind"] == "heat":
             from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedHeatSolver
             hs = DistributedHeatSolver(tolerance=case["tol"], precision_strategy=case["strategy"],
+                                       use_fused_defect_down="always",
                                        agglomerate_below=case["agg"], backend=OracleBackend())
             r = hs.solve_heat_problem(_heat_problem(dom, case.get("source", False)), nx, ny, _time_config(case))
             res = {"u": r["final_solution"], "iters": r["total_mg_iterations"], "steps": r["total_steps"],
@@ -96,6 +97,7 @@ def _worker(rank, world, port, case, out):
                    "keys": sorted(r.keys())}
         else:
             sol = DistributedMixedPrecisionSolver(nx, ny, domain=dom, precision_strategy=case["strategy"],
+                                                  use_fused_defect_down="always",
                                                   tolerance=1e-8, agglomerate_below=case["agg"], backend=OracleBackend(),
                                                   transport=transport, coefficient=coef)
             sol.set_rhs_from_global(f)

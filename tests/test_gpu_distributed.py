@@ -21,8 +21,8 @@ def test_world1_distributed_engine_equals_oracle():
     f = O.mms_rhs(n)
     for strategy, cycles in (("double", 8), ("adaptive", 8)):
         sol = DistributedMixedPrecisionSolver(n, n, precision_strategy=strategy, tolerance=1e-8, agglomerate_below=65,
-                                              device=torch.device("cuda", 0))
-        assert sol.eng.D >= 2
+                                              device=torch.device("cuda", 0), use_fused_defect_down="always")
+        assert sol.eng.D >= 2 and sol.fused_defect_down == (strategy == "adaptive")
         sol.set_rhs_from_global(torch.from_numpy(f).cuda())
         u, info = sol.solve()
         assert info["converged"] and info["iterations"] == cycles
@@ -46,7 +46,7 @@ def test_world1_distributed_heat_equals_single_gpu_heat_solver():
     for method, bound in ((TimeSteppingMethod.BACKWARD_EULER, 1e-2), (TimeSteppingMethod.CRANK_NICOLSON, 2e-4)):
         cfg = TimeSteppingConfig(method, dt=0.005, t_final=0.02)
         rd = DistributedHeatSolver(tolerance=1e-10, agglomerate_below=33, device=torch.device("cuda", 0),
-                                   use_cuda_graphs=True).solve_heat_problem(prob, n, n, cfg)
+                                   use_cuda_graphs=True, use_fused_defect_down="always").solve_heat_problem(prob, n, n, cfg)
         rs = HeatSolver2D(tolerance=1e-10).solve_heat_problem(prob, n, n, cfg)
         assert rd["total_steps"] == rs["total_steps"] == 4
         assert np.max(np.abs(rd["final_solution"] - rs["final_solution"])) <= 1e-8
@@ -127,7 +127,8 @@ def test_world1_solve_many_on_slabs_is_solve_per_right_hand_side():
     from mixed_precision_multigrid_solvers_for_pdes_b200.distributed import DistributedMixedPrecisionSolver
     n = 513
     sol = DistributedMixedPrecisionSolver(n, n, precision_strategy="adaptive", tolerance=1e-8, agglomerate_below=65,
-                                          device=torch.device("cuda", 0), use_cuda_graphs=True)
+                                          device=torch.device("cuda", 0), use_cuda_graphs=True,
+                                          use_fused_defect_down="always")
     base = torch.from_numpy(O.mms_rhs(n))
     fs = [(base * s).pin_memory() for s in (1.0, -2.5, 0.5, 3.0)]
     us = [torch.empty((n, n), dtype=torch.float64).pin_memory() for _ in fs]

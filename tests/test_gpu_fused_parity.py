@@ -371,7 +371,7 @@ def test_defect_down_refinement_matches_two_pass_refinement():
     from mixed_precision_multigrid_solvers_for_pdes_b200 import MixedPrecisionMultigrid, PoissonProblem
     hist = []
     for dd in (True, False):
-        s = MixedPrecisionMultigrid(tolerance=1e-9, use_fused_defect_down=dd)
+        s = MixedPrecisionMultigrid(tolerance=1e-9, use_fused_defect_down="always" if dd else False)
         u, info = s.solve(PoissonProblem.manufactured(1025))
         assert s._dd_ok() == dd
         hist.append((info["residual_history"], u.copy()))
@@ -388,7 +388,8 @@ def test_last_cycle_hint_never_changes_results():
     n = 1025
     out = []
     for dd, hints in ((False, [False] * 6), (True, [False, True, True, False, True, False]), (True, [True] * 6)):
-        s = MixedPrecisionMultigrid(precision_strategy="refinement", tolerance=1e-30, use_fused_defect_down=dd,
+        s = MixedPrecisionMultigrid(precision_strategy="refinement", tolerance=1e-30,
+                                    use_fused_defect_down="always" if dd else False,
                                     use_cuda_graphs=True)
         s.setup(n, n)
         b64 = s._engine.levels[0].bufs(torch.float64)
