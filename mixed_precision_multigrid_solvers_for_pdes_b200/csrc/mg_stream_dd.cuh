@@ -7,9 +7,11 @@
 // This kernel does the first two in ONE pass: the fp32 residual row leaves for HBM (the up pass needs it as its
 // right-hand side) but is consumed by the smoothing pipeline straight from registers: 37 B / point instead of 41, one
 // launch less, and the issue-bound smoothing instructions (75 % issue utilisation on their own) run in the shadow of the
-// HBM-bound defect traffic.  Same decomposition as rbgs_stream_kernel (mg_stream.cuh): every warp owns a strip of 128
+// HBM-bound defect traffic (measured at 16385^2: 1.70-1.73 ms against 1.37 + 0.49, DRAM traffic at 0.98 of the copy peak;
+// profiles/r02_ncu_dd_16385.md).  Same decomposition as rbgs_stream_kernel (mg_stream.cuh): every warp owns a strip of 128
 // columns and streams down a tile of rows, TMA boxes of RB rows through a warp-private ring, register windows, recomputed
-// halos (8 rows / columns: 1 for the fp64 residual + 4 half-sweeps + 2 for the restriction, rounded up to even).
+// halos: 8 columns per side (1 for the fp64 residual + 4 half-sweeps + 2 for the restriction, rounded up to the 4-element
+// vectors), 6 + 6 rows (the dependence cone exactly, see DDGeometry).
 //
 // Per arriving row i (per lane 4 contiguous elements):
 //   u_new(i)  = u(i) + (double) e(i)                               -> stored (fp64)
@@ -27,7 +29,7 @@ namespace stream {
 
 struct DDGeometry {
   static constexpr int NS = 4;          // two red-black sweeps = four half-sweep stages
-  static constexpr int H = 8;           // halo rows / columns
+  static constexpr int H = 8;           // halo columns per side
   static constexpr int OWN_LO = 8, OWN_HI = STRIP - 1 - OWN_LO, STRIDE = OWN_HI - OWN_LO + 1;  // 112 owned columns
   // Rows a tile streams besides its own [I0, I1).  Dependence cone: the restricted residual centred on row I0 reads
   // residual rows >= I0-1, those read e' rows >= I0-2, four half-sweeps from a ZERO iterate reach three rows further
