@@ -1,6 +1,7 @@
 // Pipelined lexicographic Gauss-Seidel (skewed wavefront over warps): kernel + progress-counter pool, shared by
 // mg_smooth_lexgs (mg_basic.cu) and the CorrectedMultigridSolver kernels (mg_corrected.cu).
 #pragma once
+#include <mutex>
 #include "mg_common.cuh"
 
 namespace mg {
@@ -134,9 +135,11 @@ constexpr int LEXGS_SLOTS = 8, LEXGS_SLOT_INTS = 1 << 15;
 inline int* lexgs_progress(int nwarps) {
   static int* buf[64] = {nullptr};
   static unsigned next[64] = {0};
+  static std::mutex guard;  // host threads may call the entry points concurrently
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || nwarps > LEXGS_SLOT_INTS) return nullptr;
+  std::lock_guard<std::mutex> lock(guard);
   if (!buf[dev] && cudaMalloc(&buf[dev], sizeof(int) * LEXGS_SLOTS * LEXGS_SLOT_INTS) != cudaSuccess) return nullptr;
   return buf[dev] + (size_t)(next[dev]++ % LEXGS_SLOTS) * LEXGS_SLOT_INTS;
 }
