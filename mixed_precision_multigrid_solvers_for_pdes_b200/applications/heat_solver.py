@@ -25,8 +25,8 @@ import torch
 
 from .. import ops
 from ..core.grid import Grid
-from ..device import empty_field, require_cuda, to_device, to_host
-from ..problems import HeatProblem, PoissonProblem, TimeSteppingConfig, TimeSteppingMethod
+from ..device import require_cuda, to_device, to_host
+from ..problems import HeatProblem, TimeSteppingConfig, TimeSteppingMethod
 from ..solvers.mixed_precision import MixedPrecisionMultigrid
 
 

@@ -7,7 +7,7 @@ grid, 8.6 GB of host RAM at 16385^2), and norms accept CUDA tensors (reduced on 
 ``mg_sumsq``)."""
 from __future__ import annotations
 
-from typing import Optional, Tuple, Union
+from typing import Optional, Tuple
 
 import numpy as np
 

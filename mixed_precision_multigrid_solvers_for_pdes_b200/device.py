@@ -7,7 +7,7 @@ kernels need 16-byte aligned rows; n = 2^k + 1 is odd, hence the padding).
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple, Union
+from typing import Tuple, Union
 
 import numpy as np
 import torch

@@ -14,7 +14,7 @@ Two kernel sets implement the same sequence:
 No host synchronisation happens inside a cycle, so a cycle can be captured in a CUDA graph."""
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 

@@ -33,7 +33,7 @@ import torch
 
 from .. import ops
 from ..core.grid import Grid
-from ..device import empty_field, like_input, require_cuda, to_device
+from ..device import empty_field, require_cuda, to_device
 from ..operators.laplacian import HelmholtzOperator, LaplacianOperator
 from ..operators.transfer import ProlongationOperator, RestrictionOperator
 from .engine import CycleEngine
